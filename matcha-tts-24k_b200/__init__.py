@@ -1,0 +1,10 @@
+"""B200-native conditional-flow-matching decode for Matcha-TTS-24k (one hot path).
+
+Public surface:
+  CFM                      drop-in for ``matcha.models.components.flow_matching.CFM``
+  install()                patch that symbol inside an importable ``matcha`` package
+  EstimatorWeights, EstimatorConfig, weight_spec
+  native                   ctypes binding of the C-ABI library (``include/cfm_b200.h``)
+"""
+from . import synthetic  # noqa: F401
+from .estimator import EstimatorConfig, EstimatorWeights, config_from_decoder_params, weight_spec  # noqa: F401
