@@ -1,0 +1,112 @@
+/*
+ * cfm_b200.h - C ABI of the B200-native CFM decode library (libcfm_b200.so).
+ *
+ * One hot path of faltiska/Matcha-TTS-24k: the conditional-flow-matching decode, i.e. the fixed-grid ODE
+ * loop around the 1-D U-Net estimator.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository).  Plain C types only: device pointers are raw CUDA device
+ * addresses, `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success or a
+ * negative cfm_status; cfm_last_error() returns the message.  No exception or allocation crosses the ABI.
+ * Nothing here falls back to the CPU: without a CUDA device of compute capability 10.x every call fails.
+ */
+#ifndef CFM_B200_H_
+#define CFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfm_handle cfm_handle;
+
+typedef enum {
+  CFM_OK = 0,
+  CFM_ERR_INVALID = -1,   /* bad argument / unsupported configuration (host wrapper raises ValueError) */
+  CFM_ERR_CUDA = -2,      /* CUDA runtime / driver failure */
+  CFM_ERR_STATE = -3,     /* call order violated (e.g. solve before load_weights / plan) */
+  CFM_ERR_WEIGHTS = -4    /* missing, unexpected or mis-shaped parameter */
+} cfm_status;
+
+typedef enum { CFM_PREC_BF16 = 0, CFM_PREC_FP32 = 1 } cfm_precision;
+typedef enum { CFM_SOLVER_EULER = 0, CFM_SOLVER_MIDPOINT = 1, CFM_SOLVER_HEUN3 = 2, CFM_SOLVER_RK4 = 3 } cfm_solver;
+
+/* Mirrors the keyword arguments of the reference estimator constructor
+ * Decoder(in_channels, out_channels, channels, dropout, attention_head_dim, n_blocks, num_mid_blocks, num_heads)
+ * (matcha/models/components/decoder.py:203-216), as reached through
+ * CFM(in_channels, out_channel, cfm_params, decoder_params) (matcha/models/components/flow_matching.py:110-117). */
+typedef struct {
+  int32_t in_channels;   /* 2 * n_feats */
+  int32_t out_channels;  /* n_feats */
+  int32_t channels;      /* C: width of both U-Net levels */
+  int32_t n_heads;
+  int32_t head_dim;
+  int32_t n_blocks;      /* transformer blocks per stage */
+  int32_t n_mid_blocks;
+  int32_t precision;     /* cfm_precision: storage/MMA operand type; statistics, residual stream and ODE state are fp32 */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t flags;         /* CFM_FLAG_* */
+} cfm_config;
+
+#define CFM_FLAG_NO_GRAPH 1      /* launch kernels directly instead of replaying the captured CUDA graph */
+#define CFM_FLAG_SIMT_GEMM 2     /* debug: run every GEMM on the fp32-FMA kernel instead of tcgen05 */
+#define CFM_FLAG_UNFUSED_STATS 4 /* debug: GroupNorm statistics in a separate pass instead of the GEMM epilogue */
+#define CFM_FLAG_SIMT_ATTN 8     /* debug: fp32-FMA attention kernel instead of the tensor-core kernel */
+
+/* One parameter of the estimator, named exactly as in the reference state_dict below `decoder.estimator.`
+ * (e.g. "down_blocks.0.0.block1.block.0.weight"); data = device pointer to contiguous fp32. */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} cfm_weight_desc;
+
+/* Replaces: CFM.__init__ -> Decoder.__init__ (flow_matching.py:110-117, decoder.py:202-310). */
+int cfm_create(const cfm_config* cfg, cfm_handle** out);
+void cfm_destroy(cfm_handle* h);
+const char* cfm_last_error(const cfm_handle* h); /* h may be NULL: error of the last failed cfm_create */
+
+/* Replaces: nn.Module.load_state_dict on decoder.estimator.* (matcha/inference.py:194).  Packs / casts every
+ * parameter into the library's own device layouts; must be called again whenever the parameters change.
+ * Fails with CFM_ERR_WEIGHTS if any parameter is missing, unexpected or mis-shaped (the reference loads with
+ * strict=False and would hide that). */
+int cfm_load_weights(cfm_handle* h, const cfm_weight_desc* descs, int32_t n);
+
+/* Prepares a decode of `batch` utterances padded to `t_pad` frames (t_pad even, reference
+ * matcha/utils/model.py:15-21) with valid lengths `lengths[b]` (prefix masks, reference
+ * matcha/utils/model.py:7-9) over the time grid `t_span[0..n_points)` with a torchdiffeq fixed-grid solver
+ * (call site flow_matching.py:60-63).  Builds the packed row tables, workspace and the CUDA graph of the
+ * whole ODE loop.  Replaces the per-call setup of BASECFM.solve + OdeSolverWrapper. */
+int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad, const float* t_span, int32_t n_points,
+             int32_t solver);
+
+/* Replaces: BASECFM.solve(x, t_span, mu, mask) (flow_matching.py:60-63) for the planned shapes.
+ * mu, z, out: device fp32, contiguous (batch, out_channels, t_pad).  `z` is the initial state (the injected
+ * noise); padded frames of `out` equal `z` there, exactly as in the reference where the masked velocity never
+ * moves them.  Asynchronous on `stream`. */
+int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): H2D of mu and z, solve, D2H of out, then synchronises.
+ * This is the call a non-PyTorch host (cgo / JNI / N-API) binds. */
+int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out);
+
+/* Replaces: one call of Decoder.forward(x, mask, mu, t) (decoder.py:359-426) for the planned shapes:
+ * v = estimator(x, mask, mu, t); padded frames of v are zero.  Asynchronous on `stream`. */
+int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream);
+
+/* Introspection for tests and the benchmark. */
+int cfm_plan_info(const cfm_handle* h, int64_t* rows_full, int64_t* rows_half, int64_t* n_nfe, int64_t* kernels_per_solve,
+                  int64_t* workspace_bytes);
+/* Copies a named intermediate buffer of the last estimator evaluation to the host as fp32 (debug; see cfm.cu). */
+int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max_elems, int64_t* rows, int64_t* cols);
+/* Debug: within cfm_estimator (or an ungraphed solve) skip every kernel launch after the first n (n < 0: off), so that
+ * cfm_debug_read sees the intermediate state at that point of the schedule. */
+int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches);
+/* Stand-alone tapped GEMM on caller buffers (tests of the tcgen05 kernel against the fp32-FMA kernel):
+ * D[m,n] = sum_t sum_k A[m + shift[t], k] * W[t*N + n, k]; A (M x K), W (n_taps*N x K) bf16 device, D fp32. */
+int cfm_debug_gemm(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, int32_t M, int32_t N, int32_t K,
+                   int32_t n_taps, const int32_t* shifts, int32_t use_tc, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFM_B200_H_ */

@@ -8,3 +8,6 @@ Public surface:
 """
 from . import synthetic  # noqa: F401
 from .estimator import EstimatorConfig, EstimatorWeights, config_from_decoder_params, weight_spec  # noqa: F401
+from .cfm import CFM, install, lengths_from_mask  # noqa: F401,E402
+from .sharding import gather_outputs, shard_utterances  # noqa: F401,E402
+from . import _native as native  # noqa: F401,E402

@@ -1,0 +1,227 @@
+"""Drop-in replacement for ``matcha.models.components.flow_matching.CFM`` (reference flow_matching.py:110-117).
+
+Same constructor, same ``forward(mu, mask, n_timesteps)`` call (reference matcha/inference.py:169), same mutable
+``.solver`` / ``.estimator`` attributes (reference cli.py:94, server.py:43,47,109) and the same state-dict keys below
+``estimator.``; the arithmetic runs in libcfm_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/cfm_b200.h).  There is no PyTorch or CPU fallback: CPU tensors, a missing library or a non-B200 device raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+from .estimator import EstimatorWeights, config_from_decoder_params
+
+
+def lengths_from_mask(mask: torch.Tensor):
+    """mask: (B, 1, T) or (B, T), 1.0 = valid.  Returns python ints; rejects anything that is not a prefix mask
+    (the reference only ever builds ``sequence_mask(lengths, T)``: matcha/utils/model.py:7-9, inference.py:167)."""
+    if mask.dtype == torch.bool:
+        raise ValueError("boolean masks select diffusers' masking semantics in the reference; this path implements "
+                         "the float (additive) mask every reference caller passes")
+    m = mask[:, 0, :] if mask.ndim == 3 else mask
+    T = m.shape[-1]
+    lengths = m.sum(-1).round().to(torch.int64)
+    expect = (torch.arange(T, device=m.device).unsqueeze(0) < lengths.unsqueeze(1)).to(m.dtype)
+    ok = bool(torch.equal(m, expect))
+    lengths = lengths.tolist()
+    if not ok:
+        raise ValueError("mask is not a 0/1 prefix (sequence) mask")
+    return lengths
+
+
+class CFM(torch.nn.Module):
+    def __init__(self, in_channels, out_channel, cfm_params, decoder_params, precision: Optional[str] = None,
+                 flags: int = 0):
+        super().__init__()
+        self.n_feats = in_channels  # sic: the reference passes in_channels as n_feats (flow_matching.py:112-115)
+        self.solver = cfm_params.solver
+        self.sigma_min = getattr(cfm_params, "sigma_min", 1e-4)
+        self.use_mu_prior = getattr(cfm_params, "use_mu_prior", False)
+        self.precision = precision or os.environ.get("CFM_B200_PRECISION", "bf16")
+        if self.precision not in N.PREC:
+            raise ValueError(f"precision must be one of {sorted(N.PREC)}, got {self.precision!r}")
+        self.flags = int(flags) | int(os.environ.get("CFM_B200_FLAGS", "0"))
+        cfg = config_from_decoder_params(in_channels, out_channel, **dict(decoder_params))
+        est = EstimatorWeights(cfg)
+        est._owner = [self]
+        self.estimator = est
+        # survives ``model.decoder.estimator = torch.compile(...)`` (reference server.py:47): same Parameter objects
+        object.__setattr__(self, "_weights", est)
+        object.__setattr__(self, "_handle", None)
+        object.__setattr__(self, "_weights_sig", None)
+        object.__setattr__(self, "_plan_key", None)
+        object.__setattr__(self, "_lib", None)
+
+    # ------------------------------------------------------------------ native plumbing
+    def _native(self, device: torch.device):
+        if self._handle is not None and self._device == device:
+            return self._lib, self._handle
+        self.close()
+        lib = N.load_library()
+        c = self._weights.cfg
+        cfg = N.Config(c.in_channels, c.out_channels, c.channels, c.n_heads, c.head_dim, c.n_blocks, c.n_mid_blocks,
+                       N.PREC[self.precision], device.index if device.index is not None else torch.cuda.current_device(),
+                       self.flags)
+        handle = C.c_void_p()
+        N.check(lib, None, lib.cfm_create(C.byref(cfg), C.byref(handle)))
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_handle", handle)
+        object.__setattr__(self, "_device", device)
+        object.__setattr__(self, "_weights_sig", None)
+        object.__setattr__(self, "_plan_key", None)
+        return lib, handle
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._lib is not None:
+            self._lib.cfm_destroy(self._handle)
+        object.__setattr__(self, "_handle", None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def refresh(self, device: Optional[torch.device] = None):
+        """(Re)packs the estimator parameters into the library.  Called automatically when a parameter's storage or
+        version counter changed (``load_state_dict`` and ``.to(device)`` happen after construction: inference.py:193-194)."""
+        params = list(self._weights.state_dict(keep_vars=True).items())
+        device = device or params[0][1].device
+        lib, handle = self._native(device)
+        keep, descs = [], (N.WeightDesc * len(params))()
+        for i, (name, p) in enumerate(params):
+            t = p.detach()
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            descs[i].name = name.encode()
+            descs[i].data = t.data_ptr()
+            descs[i].ndim = t.ndim
+            for j, s in enumerate(t.shape):
+                descs[i].shape[j] = s
+        torch.cuda.synchronize(device)
+        N.check(lib, handle, lib.cfm_load_weights(handle, descs, len(params)))
+        object.__setattr__(self, "_weights_sig", self._signature())
+        object.__setattr__(self, "_plan_key", None)
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self._weights.parameters())
+
+    def _ensure(self, device, lengths: Sequence[int], T: int, t_span: Sequence[float], solver: str):
+        if self.training:
+            raise RuntimeError("the CUDA decode path is inference-only (dropout sites are identity only in eval mode); "
+                               "call .eval() as the reference does at load time (matcha/inference.py:195)")
+        if solver not in N.SOLVERS:
+            raise ValueError(f"unknown ODE solver {solver!r}; supported fixed-grid solvers: {sorted(N.SOLVERS)}")
+        if self._handle is None or self._device != device or self._weights_sig != self._signature():
+            self.refresh(device)
+        lib, handle = self._lib, self._handle
+        key = (tuple(lengths), T, tuple(t_span), solver)
+        if key != self._plan_key:
+            arr = (C.c_int32 * len(lengths))(*lengths)
+            ts = (C.c_float * len(t_span))(*t_span)
+            N.check(lib, handle, lib.cfm_plan(handle, arr, len(lengths), T, ts, len(t_span), N.SOLVERS[solver]))
+            object.__setattr__(self, "_plan_key", key)
+        return lib, handle
+
+    @staticmethod
+    def _prep(x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("CFM (B200) needs CUDA tensors: there is no CPU path")
+        return x.detach().to(torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ reference surface
+    @torch.inference_mode()
+    def forward(self, mu, mask, n_timesteps, temperature: float = 1.0, spks=None, cond=None, lengths=None):
+        """reference flow_matching.py:25-58.  ``temperature``/``spks``/``cond`` are the upstream Matcha-TTS superset;
+        with their defaults this is exactly the fork's ``forward(mu, mask, n_timesteps)``."""
+        if spks is not None:
+            raise NotImplementedError("decoder speaker conditioning was removed from the fork "
+                                      "(documentation/PROBLEMS.md:41-46); not implemented in this round")
+        g = torch.Generator(device=mu.device)
+        g.manual_seed(42)
+        noise = torch.randn(mu.shape, generator=g, device=mu.device, dtype=mu.dtype)
+        if temperature != 1.0:
+            noise = noise * temperature
+        z = mu + noise if self.use_mu_prior else noise
+        t_span = torch.linspace(0, 1, n_timesteps + 1, device=mu.device)
+        return self.solve(z, t_span=t_span, mu=mu, mask=mask, lengths=lengths)
+
+    @torch.inference_mode()
+    def solve(self, x, t_span, mu, mask, lengths=None):
+        """reference flow_matching.py:60-63; ``x`` is the injected initial state z."""
+        mu_, x_ = self._prep(mu), self._prep(x)
+        B, F, T = mu_.shape
+        if x_.shape != mu_.shape or mask.shape[0] != B or mask.shape[-1] != T:
+            raise ValueError("x, mu and mask disagree on (B, F, T)")
+        if lengths is None:
+            lengths = lengths_from_mask(mask)
+        ts = [float(v) for v in t_span.detach().to(torch.float32).cpu().tolist()]
+        lib, handle = self._ensure(mu_.device, [int(v) for v in lengths], T, ts, self.solver)
+        out = torch.empty_like(mu_)
+        stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        N.check(lib, handle, lib.cfm_solve(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr(), stream))
+        return out
+
+    @torch.inference_mode()
+    def solve_host(self, x, t_span, mu, lengths, device=None):
+        """Host-buffer entry (cfm_solve_host): CPU tensors in, CPU tensor out, copies inside the library call."""
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        mu_, x_ = mu.detach().float().contiguous(), x.detach().float().contiguous()
+        B, F, T = mu_.shape
+        ts = [float(v) for v in torch.as_tensor(t_span, dtype=torch.float32).tolist()]
+        lib, handle = self._ensure(device, [int(v) for v in lengths], T, ts, self.solver)
+        out = torch.empty_like(mu_, pin_memory=mu_.is_pinned())
+        N.check(lib, handle, lib.cfm_solve_host(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr()))
+        return out
+
+    def _estimator_call(self, x, mask, mu, t):
+        mu_, x_ = self._prep(mu), self._prep(x)
+        B, F, T = mu_.shape
+        tt = torch.as_tensor(t)
+        if tt.numel() != 1:
+            raise NotImplementedError("per-sample t (training, reference flow_matching.py:84-97) is not on this path")
+        lengths = lengths_from_mask(mask)
+        lib, handle = self._ensure(mu_.device, lengths, T, [0.0, 1.0], "euler")
+        v = torch.empty_like(mu_)
+        stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        N.check(lib, handle, lib.cfm_estimator(handle, x_.data_ptr(), mu_.data_ptr(), float(tt), v.data_ptr(), stream))
+        return v
+
+    def compute_loss(self, x1, mask, mu):
+        raise NotImplementedError("training (reference flow_matching.py:65-107) is outside this build's scope: "
+                                  "the CUDA path is forward/inference only (DESIGN.md, 'out of scope')")
+
+    # ------------------------------------------------------------------ introspection (tests / bench)
+    def plan_info(self):
+        vals = [C.c_int64() for _ in range(5)]
+        N.check(self._lib, self._handle, self._lib.cfm_plan_info(self._handle, *[C.byref(v) for v in vals]))
+        keys = ("rows_full", "rows_half", "n_nfe", "kernels_per_solve", "workspace_bytes")
+        return dict(zip(keys, (v.value for v in vals)))
+
+    def debug_read(self, name: str) -> torch.Tensor:
+        r, c = C.c_int64(), C.c_int64()
+        N.check(self._lib, self._handle, self._lib.cfm_debug_read(self._handle, name.encode(), None, 0, C.byref(r), C.byref(c)))
+        out = torch.empty(r.value, c.value, dtype=torch.float32)
+        N.check(self._lib, self._handle,
+                self._lib.cfm_debug_read(self._handle, name.encode(), out.data_ptr(), out.numel(), C.byref(r), C.byref(c)))
+        return out
+
+
+def install():
+    """Makes ``from matcha.models.components.flow_matching import CFM`` resolve to this class, so that
+    matcha.inference / cli.py / server.py run unchanged (reference import sites: inference.py:6, matcha_tts.py:7)."""
+    import importlib
+
+    mod = importlib.import_module("matcha.models.components.flow_matching")
+    mod.CFM = CFM
+    for name in ("matcha.inference", "matcha.models.matcha_tts"):
+        import sys
+        if name in sys.modules and hasattr(sys.modules[name], "CFM"):
+            sys.modules[name].CFM = CFM
+    return CFM

@@ -1,0 +1,262 @@
+// Tensor-core flash attention for sm_100a (bf16, head_dim 64): softmax(Q K^T d^-1/2 + key_bias) V per (utterance, head).
+//
+// One CTA per (utterance, head, 128-query tile); 192 threads = TMA warp, MMA warp, 4 softmax warps (one query row per
+// thread).  Per 128-key tile:
+//     S  = Q K^T      tcgen05.mma  M128 N128 K64   (Q, K tiles K-major, 128B-swizzled by TMA)    -> TMEM cols [0,128)
+//     P  = exp2(...)  tcgen05.ld S -> registers -> online softmax -> bf16 P written to smem in the UMMA K-major layout
+//     PV = P V        tcgen05.mma  M128 N64 K128   (V tile MN-major straight from TMA)            -> TMEM cols [128,192)
+//     O  = O*corr + PV in registers (tcgen05.ld)
+// Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// The per-key bias implements the reference's additive float mask in the packed formulation (attn.cuh header).
+#pragma once
+#include <cuda.h>
+#include <string>
+
+#include "attn.cuh"
+#include "ptx.cuh"
+
+namespace cfm {
+
+struct AttnTcCfg {
+  static constexpr int D = 64, QT = 128, KT = 128;
+  static constexpr int Q_BYTES = QT * D * 2, K_BYTES = KT * D * 2, V_BYTES = KT * D * 2, P_BYTES = QT * KT * 2;
+  static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int THREADS = 192;
+  static constexpr int TMEM_COLS = 256;
+};
+
+__global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttTable* __restrict__ utt,
+               const int4* __restrict__ work, bf16* __restrict__ out, long long ldo, float scale_log2) {
+  using Cfg = AttnTcCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t *bar_q = bars + 0, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_p = bars + 4, *bar_pv = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int4 w = work[blockIdx.x];
+  const UttTable u = utt[w.x];
+  const int head = w.y, q0 = w.z;
+  const int L = u.len, nk = u.len + 1;
+  const int n_tiles = (nk + Cfg::KT - 1) / Cfg::KT;
+  const int row0 = u.start;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_qkv);
+    ptx::mbar_init(bar_q, 1);
+    ptx::mbar_init(bar_k, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, 128);
+    ptx::mbar_init(bar_pv, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_qkv, bar_q, head * Cfg::D, row0 + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j > 0) ptx::mbar_wait(bar_s, (j - 1) & 1);  // S_{j-1} issued & complete: K buffer free
+        ptx::mbar_expect_tx(bar_k, Cfg::K_BYTES);
+        ptx::tma_load_2d(smem + Cfg::OFF_K, &tm_qkv, bar_k, inner + head * Cfg::D, row0 + j * Cfg::KT);
+        if (j > 0) ptx::mbar_wait(bar_pv, (j - 1) & 1);  // PV_{j-1} complete: V buffer free
+        ptx::mbar_expect_tx(bar_v, Cfg::V_BYTES);
+        ptx::tma_load_2d(smem + Cfg::OFF_V, &tm_qkv, bar_v, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0);
+      constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 64, 1);  // B (= V tile) is MN-major
+      const uint32_t q_addr = ptx::smem_u32(smem + Cfg::OFF_Q), k_addr = ptx::smem_u32(smem + Cfg::OFF_K);
+      const uint32_t v_addr = ptx::smem_u32(smem + Cfg::OFF_V), p_addr = ptx::smem_u32(smem + Cfg::OFF_P);
+      ptx::mbar_wait(bar_q, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = j & 1;
+        ptx::mbar_wait(bar_k, ph);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16(tmem_s, ptx::umma_desc_sw128(q_addr + k * 32), ptx::umma_desc_sw128(k_addr + k * 32), idesc_s, k > 0);
+        ptx::umma_commit(bar_s);
+        ptx::mbar_wait(bar_p, ph);  // P_j in smem, S_j and PV_{j-1} drained from TMEM
+        ptx::mbar_wait(bar_v, ph);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + (k >> 2) * (Cfg::QT * 128) + (k & 3) * 32),
+                         ptx::umma_desc_sw128(v_addr + k * 2048), idesc_pv, k > 0);
+        ptx::umma_commit(bar_pv);
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue: one query row per thread
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const float pad_bias = u.pad_key_bias * 1.4426950408889634f;
+    float o[Cfg::D];
+#pragma unroll
+    for (int d = 0; d < Cfg::D; ++d) o[d] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+    uint8_t* p_row = smem + Cfg::OFF_P + r * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const int k0 = j * Cfg::KT;
+      const bool ragged = (k0 + Cfg::KT > L);  // tile holds the pad token and/or rows past this utterance
+      ptx::mbar_wait(bar_s, ph);
+      ptx::tc_fence_after();
+      // pass 1: row maximum
+      float mt = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < Cfg::KT; c += 32) {
+        uint32_t a[16], b[16];
+        ptx::tmem_ld16(tmem_s + lane_off + c, a);
+        ptx::tmem_ld16(tmem_s + lane_off + c + 16, b);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]) * scale_log2;
+          if (ragged) {
+            const int key = k0 + c + i;
+            t = key < L ? t : (key == L ? t + pad_bias : -INFINITY);
+          }
+          mt = fmaxf(mt, t);
+        }
+      }
+      const float mnew = fmaxf(mrun, mt);
+      const float corr = exp2f(mrun - mnew);
+      float psum = 0.f;
+      // pass 2: P = exp2(t - m) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7))
+#pragma unroll 1
+      for (int c = 0; c < Cfg::KT; c += 32) {
+        uint32_t a[16], b[16];
+        ptx::tmem_ld16(tmem_s + lane_off + c, a);
+        ptx::tmem_ld16(tmem_s + lane_off + c + 16, b);
+        ptx::tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]) * scale_log2;
+          if (ragged) {
+            const int key = k0 + c + i;
+            t = key < L ? t : (key == L ? t + pad_bias : -INFINITY);
+          }
+          p[i] = exp2f(t - mnew);
+          psum += p[i];
+        }
+        uint8_t* blk = p_row + (c >> 6) * (Cfg::QT * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = ((c & 63) >> 3) + g;
+          uint4 pk;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(p[8 * g + 0], p[8 * g + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(p[8 * g + 2], p[8 * g + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p[8 * g + 4], p[8 * g + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(p[8 * g + 6], p[8 * g + 7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2);
+          pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      lrun = lrun * corr + psum;
+      mrun = mnew;
+#pragma unroll
+      for (int d = 0; d < Cfg::D; ++d) o[d] *= corr;
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      ptx::mbar_arrive(bar_p);
+      ptx::mbar_wait(bar_pv, ph);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < Cfg::D; c += 32) {
+        uint32_t a[16], b[16];
+        ptx::tmem_ld16(tmem_pv + lane_off + c, a);
+        ptx::tmem_ld16(tmem_pv + lane_off + c + 16, b);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          o[c + i] += __uint_as_float(a[i]);
+          o[c + 16 + i] += __uint_as_float(b[i]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    const int qi = q0 + r;
+    if (qi < nk) {
+      const float inv = 1.f / lrun;
+      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
+#pragma unroll
+      for (int d = 0; d < Cfg::D; d += 8) {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[d + 0] * inv, o[d + 1] * inv);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[d + 4] * inv, o[d + 5] * inv);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(o[d + 6] * inv, o[d + 7] * inv);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + d) = pk;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+inline int attn_tc_set_attr(std::string* err) {
+  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    *err = std::string("cudaFuncSetAttribute(attn_tc_kernel): ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+template <typename Enc>
+inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, int M, const UttTable* utt, const int4* work,
+                          int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err) {
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled failed for the attention QKV map";
+    return -2;
+  }
+  attn_tc_kernel<<<n_work, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, s>>>(tm, inner, utt, work, static_cast<bf16*>(out), ldo,
+                                                                           scale * 1.4426950408889634f);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace cfm

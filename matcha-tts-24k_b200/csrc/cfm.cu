@@ -1,0 +1,1140 @@
+// libcfm_b200: C-ABI implementation (include/cfm_b200.h).  Host side of the CFM decode: weight packing, the
+// pad-aware packed row tables, the per-NFE kernel schedule of the U-Net estimator (reference decoder.py:359-426),
+// the fixed-grid ODE stages (reference flow_matching.py:60-63 -> torchdiffeq) and the CUDA graph around them.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/cfm_b200.h"
+#include "attn.cuh"
+#include "attn_tc.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace cfm;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string g_create_error;
+
+struct GemmW {  // one packed GEMM weight: [n_taps * n_stride, Kp] in the activation type, K-major
+  void* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0, Kp = 0, n_taps = 1, n_stride = 0;
+};
+struct NormW {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+  double* bias_gsum = nullptr;  // GroupNorm sites only: per-group (sum b, sum b^2) of the preceding conv bias
+};
+struct ResnetW {
+  GemmW conv1, conv2, res;
+  NormW gn1, gn2;
+  float *mlp_w = nullptr, *mlp_b = nullptr;
+};
+struct BlockW {
+  NormW ln1, ln3;
+  GemmW qkv, out, ff1, ff2;
+  float *ea = nullptr, *ib = nullptr;
+};
+struct StageW {
+  ResnetW res;
+  std::vector<BlockW> blocks;
+};
+struct Model {
+  float *t1_w = nullptr, *t1_b = nullptr, *t2_w = nullptr, *t2_b = nullptr;
+  std::vector<StageW> stages;  // down0, down1, mid..., up0, up1
+  GemmW down_s2, down_tail, up_even, up_odd, up_tail, final_conv, final_proj;
+  NormW final_gn;
+};
+
+struct OdeStage {
+  float t;
+  float c_v;
+  float c_k[3];
+  int kin[3];  // index of stored k buffer or -1
+  int kout;    // -1: not stored
+  bool write_state;
+};
+
+struct Plan {
+  int B = 0, T = 0;
+  std::vector<int> L;
+  int M1 = 0, M2 = 0;
+  std::vector<OdeStage> stages;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  // tables
+  UttTable *utt1 = nullptr, *utt2 = nullptr;
+  int *info1 = nullptr, *info2 = nullptr;
+  int4 *work1 = nullptr, *work2 = nullptr;
+  int n_work1 = 0, n_work2 = 0;
+  // time embedding
+  float *tvals = nullptr, *sinemb = nullptr, *temb_a = nullptr, *temb = nullptr, *tproj = nullptr;
+  // state
+  float *xstate = nullptr, *vout = nullptr, *kbuf[3] = {nullptr, nullptr, nullptr};
+  double* stats = nullptr;
+  size_t stats_bytes = 0;
+  // activations per resolution (index 0 = full, 1 = half)
+  void* xin = nullptr;
+  int xin_ld = 0;
+  float *hraw[2], *rres[2], *X[2];
+  void *hact[2], *Xn[2], *qkv[2], *ao[2], *ffh[2], *sin_[2], *cat[2];
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long launches_per_solve = 0;
+};
+
+}  // namespace
+
+struct cfm_handle {
+  cfm_config cfg;
+  bool bf = true;
+  int es = 2;
+  std::string err;
+  std::vector<void*> wallocs;
+  Model model;
+  bool weights_loaded = false;
+  Plan* plan = nullptr;
+  EncodeTiledFn encode = nullptr;
+  int sm_count = 148;
+  long long launch_counter = 0;
+  long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
+  bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
+  cudaStream_t own_stream = nullptr;
+  int C() const { return cfg.channels; }
+  int inner() const { return cfg.n_heads * cfg.head_dim; }
+};
+
+namespace {
+
+int fail(cfm_handle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                                  \
+  do {                                                                                                            \
+    cudaError_t e_ = (call);                                                                                      \
+    if (e_ != cudaSuccess) return fail(h, CFM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(expr)          \
+  do {                     \
+    int r_ = (expr);       \
+    if (r_ != 0) return r_; \
+  } while (0)
+
+inline int roundup(int x, int m) { return (x + m - 1) / m * m; }
+inline void* act_off(void* p, long long elems, int es) { return static_cast<char*>(p) + elems * es; }
+inline const void* act_off(const void* p, long long elems, int es) { return static_cast<const char*>(p) + elems * es; }
+
+int dev_alloc(cfm_handle* h, std::vector<void*>& arena, void** out, size_t bytes, size_t* total = nullptr) {
+  bytes = (bytes + 1023) / 1024 * 1024;
+  if (bytes == 0) bytes = 1024;
+  CK(cudaMalloc(out, bytes));
+  CK(cudaMemset(*out, 0, bytes));
+  arena.push_back(*out);
+  if (total) *total += bytes;
+  return 0;
+}
+template <typename P>
+int dev_alloc_t(cfm_handle* h, std::vector<void*>& arena, P** out, size_t count, size_t* total = nullptr) {
+  return dev_alloc(h, arena, reinterpret_cast<void**>(out), count * sizeof(P), total);
+}
+void free_arena(std::vector<void*>& arena) {
+  for (void* p : arena) cudaFree(p);
+  arena.clear();
+}
+
+void free_plan(cfm_handle* h) {
+  if (!h->plan) return;
+  if (h->plan->exec) cudaGraphExecDestroy(h->plan->exec);
+  if (h->plan->graph) cudaGraphDestroy(h->plan->graph);
+  free_arena(h->plan->allocs);
+  delete h->plan;
+  h->plan = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+struct DescMap {
+  std::map<std::string, const cfm_weight_desc*> by_name;
+  std::map<std::string, bool> used;
+};
+
+int want(cfm_handle* h, DescMap& dm, const std::string& name, std::initializer_list<long long> shape, const float** out) {
+  auto it = dm.by_name.find(name);
+  if (it == dm.by_name.end()) return fail(h, CFM_ERR_WEIGHTS, "missing parameter '%s'", name.c_str());
+  const cfm_weight_desc* d = it->second;
+  bool ok = d->ndim == (int)shape.size();
+  int i = 0;
+  for (long long s : shape) ok = ok && d->shape[i++] == s;
+  if (!ok) return fail(h, CFM_ERR_WEIGHTS, "parameter '%s' has the wrong shape", name.c_str());
+  if (d->data == nullptr) return fail(h, CFM_ERR_WEIGHTS, "parameter '%s' has a null data pointer", name.c_str());
+  dm.used[name] = true;
+  *out = d->data;
+  return 0;
+}
+
+int copy_f32(cfm_handle* h, const float* src, size_t n, float** out) {
+  CKR(dev_alloc_t(h, h->wallocs, out, n));
+  CK(cudaMemcpy(*out, src, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
+// Pack src (fp32) into rows [row0, row0 + N) of each tap block of an already allocated GemmW.
+int pack_into(cfm_handle* h, GemmW& g, const float* src, long long s_n, long long s_k, long long s_t, int4 tap_k, int N,
+              int row0) {
+  long long total = (long long)N * g.Kp * g.n_taps;
+  int threads = 256;
+  int blocks = (int)((total + threads - 1) / threads);
+  if (h->bf)
+    pack_weight_kernel<bf16><<<blocks, threads>>>(src, s_n, s_k, s_t, g.n_taps, tap_k, N, g.K,
+                                                  static_cast<bf16*>(g.w) + (long long)row0 * g.Kp, g.Kp, g.n_stride);
+  else
+    pack_weight_kernel<float><<<blocks, threads>>>(src, s_n, s_k, s_t, g.n_taps, tap_k, N, g.K,
+                                                   static_cast<float*>(g.w) + (long long)row0 * g.Kp, g.Kp, g.n_stride);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int alloc_gemm(cfm_handle* h, GemmW& g, int N, int K, int n_taps) {
+  g.N = N, g.K = K, g.Kp = roundup(K, 64), g.n_taps = n_taps, g.n_stride = roundup(N, 64);
+  CKR(dev_alloc(h, h->wallocs, &g.w, (size_t)g.n_taps * g.n_stride * g.Kp * h->es));
+  return 0;
+}
+
+int load_linear(cfm_handle* h, DescMap& dm, const std::string& name, int N, int K, bool has_bias, GemmW& g) {
+  const float* w;
+  CKR(want(h, dm, name + ".weight", {N, K}, &w));
+  CKR(alloc_gemm(h, g, N, K, 1));
+  CKR(pack_into(h, g, w, K, 1, 0, make_int4(0, 0, 0, 0), N, 0));
+  if (has_bias) {
+    const float* b;
+    CKR(want(h, dm, name + ".bias", {N}, &b));
+    CKR(copy_f32(h, b, N, &g.bias));
+  }
+  return 0;
+}
+
+int load_conv(cfm_handle* h, DescMap& dm, const std::string& name, int N, int K, int kw, GemmW& g) {
+  const float *w, *b;
+  CKR(want(h, dm, name + ".weight", {N, K, kw}, &w));
+  CKR(want(h, dm, name + ".bias", {N}, &b));
+  CKR(alloc_gemm(h, g, N, K, kw));
+  CKR(pack_into(h, g, w, (long long)K * kw, kw, 1, make_int4(0, 1, 2, 3), N, 0));
+  CKR(copy_f32(h, b, N, &g.bias));
+  return 0;
+}
+
+int load_norm(cfm_handle* h, DescMap& dm, const std::string& name, int C, NormW& n, const float* conv_bias) {
+  const float *g, *b;
+  CKR(want(h, dm, name + ".weight", {C}, &g));
+  CKR(want(h, dm, name + ".bias", {C}, &b));
+  CKR(copy_f32(h, g, C, &n.gamma));
+  CKR(copy_f32(h, b, C, &n.beta));
+  if (conv_bias) {
+    CKR(dev_alloc_t(h, h->wallocs, &n.bias_gsum, 16));
+    bias_group_sums_kernel<<<1, 32>>>(conv_bias, C, C / 8, n.bias_gsum);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int load_resnet(cfm_handle* h, DescMap& dm, const std::string& p, int cin, ResnetW& r) {
+  const int C = h->C(), T4 = 4 * C;
+  const float *mw, *mb;
+  CKR(want(h, dm, p + ".mlp.1.weight", {C, T4}, &mw));
+  CKR(want(h, dm, p + ".mlp.1.bias", {C}, &mb));
+  CKR(copy_f32(h, mw, (size_t)C * T4, &r.mlp_w));
+  CKR(copy_f32(h, mb, C, &r.mlp_b));
+  CKR(load_conv(h, dm, p + ".block1.block.0", C, cin, 3, r.conv1));
+  CKR(load_norm(h, dm, p + ".block1.block.1", C, r.gn1, r.conv1.bias));
+  CKR(load_conv(h, dm, p + ".block2.block.0", C, C, 3, r.conv2));
+  CKR(load_norm(h, dm, p + ".block2.block.1", C, r.gn2, r.conv2.bias));
+  CKR(load_conv(h, dm, p + ".res_conv", C, cin, 1, r.res));
+  return 0;
+}
+
+int load_block(cfm_handle* h, DescMap& dm, const std::string& p, BlockW& b) {
+  const int C = h->C(), I = h->inner();
+  CKR(load_norm(h, dm, p + ".norm1", C, b.ln1, nullptr));
+  CKR(load_norm(h, dm, p + ".norm3", C, b.ln3, nullptr));
+  const float *wq, *wk, *wv;
+  CKR(want(h, dm, p + ".attn1.to_q.weight", {I, C}, &wq));
+  CKR(want(h, dm, p + ".attn1.to_k.weight", {I, C}, &wk));
+  CKR(want(h, dm, p + ".attn1.to_v.weight", {I, C}, &wv));
+  CKR(alloc_gemm(h, b.qkv, 3 * I, C, 1));
+  CKR(pack_into(h, b.qkv, wq, C, 1, 0, make_int4(0, 0, 0, 0), I, 0));
+  CKR(pack_into(h, b.qkv, wk, C, 1, 0, make_int4(0, 0, 0, 0), I, I));
+  CKR(pack_into(h, b.qkv, wv, C, 1, 0, make_int4(0, 0, 0, 0), I, 2 * I));
+  CKR(load_linear(h, dm, p + ".attn1.to_out.0", C, I, true, b.out));
+  const std::string ff = p + ".ff._orig_mod.net";
+  CKR(load_linear(h, dm, ff + ".0.proj", 4 * C, C, true, b.ff1));
+  CKR(load_linear(h, dm, ff + ".2", C, 4 * C, true, b.ff2));
+  const float *al, *be;
+  CKR(want(h, dm, ff + ".0.alpha", {4 * C}, &al));
+  CKR(want(h, dm, ff + ".0.beta", {4 * C}, &be));
+  CKR(dev_alloc_t(h, h->wallocs, &b.ea, 4 * C));
+  CKR(dev_alloc_t(h, h->wallocs, &b.ib, 4 * C));
+  snake_consts_kernel<<<(4 * C + 255) / 256, 256>>>(al, be, 4 * C, b.ea, b.ib);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int load_stage(cfm_handle* h, DescMap& dm, const std::string& p, int cin, StageW& s) {
+  CKR(load_resnet(h, dm, p + ".0", cin, s.res));
+  s.blocks.resize(h->cfg.n_blocks);
+  for (int j = 0; j < h->cfg.n_blocks; ++j) CKR(load_block(h, dm, p + ".1." + std::to_string(j), s.blocks[j]));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+int make_tmap(cfm_handle* h, CUtensorMap* tm, const void* base, long long inner_elems, long long outer_rows,
+              long long row_stride_bytes, int box_inner, int box_outer) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner_elems, (cuuint64_t)outer_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, CFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld stride=%lld box=%dx%d", (int)r,
+                inner_elems, outer_rows, row_stride_bytes, box_inner, box_outer);
+  return 0;
+}
+
+int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 192;
+}
+
+template <int BN>
+int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
+                 cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
+  const int grid = std::min(tiles, h->sm_count);
+  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(a0, a1, w, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+int set_tc_attr(cfm_handle* h) {
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+  return 0;
+}
+
+// A sources: p.A / p.lda / p.a_rows already describe element-addressed matrices.
+int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const bool tc = h->bf && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  if (!tc) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
+    if (h->bf)
+      gemm_simt_kernel<bf16><<<grid, 256, 0, s>>>(p);
+    else
+      gemm_simt_kernel<float><<<grid, 256, 0, s>>>(p);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (p.K % 64 != 0) return fail(h, CFM_ERR_INVALID, "tensor-core GEMM needs K %% 64 == 0 (K=%d)", p.K);
+  const int bn = pick_bn(p.N);
+  CUtensorMap tmA[2], tmW;
+  for (int i = 0; i < 2; ++i) {
+    const int src = p.A[i] ? i : 0;
+    CKR(make_tmap(h, &tmA[i], p.A[src], p.lda[src], p.a_rows[src], p.lda[src] * 2, 64, 128));
+  }
+  CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, bn));
+  switch (bn) {
+    case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, p, s);
+    case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
+    case 160: return launch_tc_bn<160>(h, tmA[0], tmA[1], tmW, p, s);
+    case 192: return launch_tc_bn<192>(h, tmA[0], tmA[1], tmW, p, s);
+    default: return launch_tc_bn<256>(h, tmA[0], tmA[1], tmW, p, s);
+  }
+}
+
+// Common part of a GEMM call: one A matrix, `w.n_taps` taps with the given row shifts / A column offsets.
+GemmParams gemm_base(int M, const void* A, long long lda, int a_rows, const GemmW& w, const int* shifts, const int* acols) {
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.M = M, p.N = w.N, p.K = w.Kp, p.n_taps = w.n_taps;
+  for (int t = 0; t < w.n_taps; ++t) {
+    p.taps[t].a_src = 0;
+    p.taps[t].row_shift = shifts ? shifts[t] : 0;
+    p.taps[t].a_col = acols ? acols[t] : 0;
+    p.taps[t].w_row = t * w.n_stride;
+  }
+  p.A[0] = A, p.lda[0] = lda, p.a_rows[0] = a_rows;
+  p.W = w.w, p.ldw = w.Kp, p.w_rows = w.n_taps * w.n_stride;
+  p.bias = w.bias;
+  p.row_mul = 1, p.row_add = 0;
+  return p;
+}
+
+struct Res {  // per-resolution view of the plan
+  int M;
+  UttTable* utt;
+  int* info;
+  int4* work;
+  int n_work;
+  float *hraw, *rres, *X;
+  void *hact, *Xn, *qkv, *ao, *ffh, *sin_, *cat;
+};
+Res res_of(Plan* pl, int r) {
+  Res v;
+  v.M = r == 0 ? pl->M1 : pl->M2;
+  v.utt = r == 0 ? pl->utt1 : pl->utt2;
+  v.info = r == 0 ? pl->info1 : pl->info2;
+  v.work = r == 0 ? pl->work1 : pl->work2;
+  v.n_work = r == 0 ? pl->n_work1 : pl->n_work2;
+  v.hraw = pl->hraw[r], v.rres = pl->rres[r], v.X = pl->X[r];
+  v.hact = pl->hact[r], v.Xn = pl->Xn[r], v.qkv = pl->qkv[r], v.ao = pl->ao[r], v.ffh = pl->ffh[r];
+  v.sin_ = pl->sin_[r], v.cat = pl->cat[r];
+  return v;
+}
+
+int run_gn_apply(cfm_handle* h, const Res& R, const NormW& gn, const double* stats, const float* addvec, const float* resid,
+                 float* out_f32, void* out_act, long long ld_act, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const int C = h->C();
+  const long long items = (long long)R.M * (C / 4);
+  const int blocks = (int)((items + 255) / 256);
+  if (h->bf)
+    gn_apply_kernel<bf16, false><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, R.utt, stats, gn.bias_gsum, gn.gamma,
+                                                        gn.beta, addvec, resid, C, out_f32, C, static_cast<bf16*>(out_act),
+                                                        ld_act);
+  else
+    gn_apply_kernel<float, true><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, R.utt, stats, gn.bias_gsum, gn.gamma,
+                                                        gn.beta, addvec, resid, C, out_f32, C, static_cast<float*>(out_act),
+                                                        ld_act);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Conv k=3 (+bias) -> fp32 raw output + GroupNorm statistics for site `site`.
+int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long long lda, const GemmW& w, int site,
+                   cudaStream_t s) {
+  static const int shifts[3] = {-1, 0, 1};
+  GemmParams p = gemm_base(R.M, A, lda, R.M, w, shifts, nullptr);
+  p.mode = EPI_STATS;
+  p.out_f32 = R.hraw, p.ld_f32 = h->C();
+  p.row_info = R.info;
+  p.stats = pl->stats + (long long)site * pl->B * 16;
+  p.group_ch = h->C() / 8;
+  const bool tc = h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  p.fused_stats = (tc && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS)) ? 1 : 0;
+  CKR(launch_gemm(h, p, true, s));
+  if (!p.fused_stats && !h->stopped()) {
+    h->launch_counter++;
+    const int items = R.M * 8;
+    gn_stats_kernel<<<(items + 255) / 256, 256, 0, s>>>(R.hraw, h->C(), R.M, h->C(), h->C() / 8, R.info, p.stats);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int run_layernorm(cfm_handle* h, const Res& R, const NormW& ln, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const int C = h->C();
+  const int blocks = (R.M * 32 + 255) / 256;
+  if (h->bf)
+    layernorm_kernel<bf16, 16><<<blocks, 256, 0, s>>>(R.X, C, R.M, C, ln.gamma, ln.beta, static_cast<bf16*>(R.Xn), C);
+  else
+    layernorm_kernel<float, 16><<<blocks, 256, 0, s>>>(R.X, C, R.M, C, ln.gamma, ln.beta, static_cast<float*>(R.Xn), C);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const int I = h->inner(), D = h->cfg.head_dim;
+  const float scale = 1.0f / sqrtf((float)D);
+  const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
+  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err);
+  if (h->bf) {
+    if (D == 64)
+      attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
+                                                          static_cast<bf16*>(R.ao), I, scale);
+    else
+      attn_simt_kernel<bf16, 32><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
+                                                          static_cast<bf16*>(R.ao), I, scale);
+  } else {
+    if (D == 64)
+      attn_simt_kernel<float, 64><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv), 3LL * I, I, R.utt, R.work,
+                                                           static_cast<float*>(R.ao), I, scale);
+    else
+      attn_simt_kernel<float, 32><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv), 3LL * I, I, R.utt, R.work,
+                                                           static_cast<float*>(R.ao), I, scale);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ResnetBlock1D (reference decoder.py:48-63) on masked input A (K columns) -> fp32 residual stream R.X.
+int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const void* A, long long lda, int& site,
+               const float* tproj, cudaStream_t s) {
+  const int C = h->C();
+  CKR(run_conv_stats(h, pl, R, A, lda, w.conv1, site, s));
+  {  // res_conv (1x1) on the same masked input -> fp32
+    GemmParams p = gemm_base(R.M, A, lda, R.M, w.res, nullptr, nullptr);
+    p.mode = EPI_STATS, p.fused_stats = 0;
+    p.out_f32 = R.rres, p.ld_f32 = C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  CKR(run_gn_apply(h, R, w.gn1, pl->stats + (long long)site * pl->B * 16, tproj, nullptr, nullptr, R.hact, C, s));
+  site++;
+  CKR(run_conv_stats(h, pl, R, R.hact, C, w.conv2, site, s));
+  CKR(run_gn_apply(h, R, w.gn2, pl->stats + (long long)site * pl->B * 16, nullptr, R.rres, R.X, nullptr, 0, s));
+  site++;
+  return 0;
+}
+
+// BasicTransformerBlock (reference transformer.py:230-303).  If copy_dst != nullptr the FF2 epilogue also writes the
+// masked activation-type copy of the block output there (skip connection / next conv input).
+int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s) {
+  const int C = h->C(), I = h->inner();
+  CKR(run_layernorm(h, R, w.ln1, s));
+  {
+    GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.qkv, nullptr, nullptr);
+    p.mode = EPI_STORE, p.out_act = R.qkv, p.ld_act = 3 * I;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  CKR(run_attention(h, R, s));
+  {
+    GemmParams p = gemm_base(R.M, R.ao, I, R.M, w.out, nullptr, nullptr);
+    p.mode = EPI_RESID, p.resid = R.X, p.ld_resid = C, p.out_f32 = R.X, p.ld_f32 = C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  CKR(run_layernorm(h, R, w.ln3, s));
+  {
+    GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.ff1, nullptr, nullptr);
+    p.mode = EPI_SNAKE, p.ea = w.ea, p.ib = w.ib, p.out_act = R.ffh, p.ld_act = 4 * C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  {
+    GemmParams p = gemm_base(R.M, R.ffh, 4 * C, R.M, w.ff2, nullptr, nullptr);
+    p.mode = EPI_RESID, p.resid = R.X, p.ld_resid = C, p.out_f32 = R.X, p.ld_f32 = C;
+    p.out_act = copy_dst, p.ld_act = copy_ld, p.row_info = R.info;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  return 0;
+}
+
+int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void* A, long long lda, int& site,
+              const float* tproj, void* copy_dst, long long copy_ld, cudaStream_t s) {
+  CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, s));
+  for (size_t j = 0; j < w.blocks.size(); ++j) {
+    const bool last = j + 1 == w.blocks.size();
+    CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s));
+  }
+  return 0;
+}
+
+// One estimator evaluation + the ODE stage update fused in final_proj's epilogue.
+int emit_nfe(cfm_handle* h, Plan* pl, int nfe_index, const OdeStage& st, float* out_f32_override, cudaStream_t s) {
+  const int C = h->C(), F = h->cfg.out_channels, es = h->es;
+  const Model& m = h->model;
+  Res R1 = res_of(pl, 0), R2 = res_of(pl, 1);
+  h->launch_counter++;
+  CK(cudaMemsetAsync(pl->stats, 0, pl->stats_bytes, s));
+  int site = 0;
+  int stage_i = 0;
+  const int n_res = 4 + h->cfg.n_mid_blocks;
+  auto tproj = [&](int r) { return pl->tproj + ((long long)nfe_index * n_res + r) * C; };
+
+  // down 0 (full resolution): [x | mu] -> X1; masked copy of the stage output -> right half of cat1 (skip h0)
+  CKR(run_stage(h, pl, R1, m.stages[stage_i], pl->xin, pl->xin_ld, site, tproj(stage_i), act_off(R1.cat, C, es), 2 * C, s));
+  stage_i++;
+  {  // Downsample1D: Conv1d k3 s2 p1 on the masked skip, rows viewed in pairs [M2, 4C]
+    const int shifts[3] = {-1, 0, 0};
+    const int acols[3] = {3 * C, C, 3 * C};
+    GemmParams p = gemm_base(R2.M, R1.cat, 4LL * C, R2.M, m.down_s2, shifts, acols);
+    p.mode = EPI_MASK, p.row_info = R2.info, p.out_act = R2.sin_, p.ld_act = C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  // down 1 (half resolution); masked copy -> right half of cat2 (skip h1)
+  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), act_off(R2.cat, C, es), 2 * C, s));
+  stage_i++;
+  {  // stage-final Conv1d k3 on the masked skip
+    const int shifts[3] = {-1, 0, 1};
+    const int acols[3] = {C, C, C};
+    GemmParams p = gemm_base(R2.M, R2.cat, 2LL * C, R2.M, m.down_tail, shifts, acols);
+    p.mode = EPI_MASK, p.row_info = R2.info, p.out_act = R2.sin_, p.ld_act = C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  for (int i = 0; i < h->cfg.n_mid_blocks; ++i) {
+    const bool last = i + 1 == h->cfg.n_mid_blocks;
+    void* dst = last ? R2.cat : R2.sin_;  // last mid block feeds the left half of cat2
+    CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), dst, last ? 2 * C : C, s));
+    stage_i++;
+  }
+  // up 0 (half resolution) on [x | h1]
+  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.cat, 2 * C, site, tproj(stage_i), R2.sin_, C, s));
+  stage_i++;
+  for (int phase = 0; phase < 2; ++phase) {  // ConvTranspose1d k4 s2 p1 as two interleaved 2-tap GEMMs
+    const int sh_even[2] = {-1, 0}, sh_odd[2] = {0, 1};
+    GemmParams p = gemm_base(R2.M, R2.sin_, C, R2.M, phase == 0 ? m.up_even : m.up_odd, phase == 0 ? sh_even : sh_odd, nullptr);
+    p.mode = EPI_MASK, p.row_info = R1.info, p.row_mul = 2, p.row_add = phase;
+    p.out_act = act_off(R1.cat, (long long)phase * 2 * C, es), p.ld_act = 4 * C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  // up 1 (full resolution) on [x | h0]
+  CKR(run_stage(h, pl, R1, m.stages[stage_i], R1.cat, 2 * C, site, tproj(stage_i), R1.sin_, C, s));
+  stage_i++;
+  {  // stage-final Conv1d k3
+    const int shifts[3] = {-1, 0, 1};
+    GemmParams p = gemm_base(R1.M, R1.sin_, C, R1.M, m.up_tail, shifts, nullptr);
+    p.mode = EPI_MASK, p.row_info = R1.info, p.out_act = R1.hact, p.ld_act = C;
+    CKR(launch_gemm(h, p, true, s));
+  }
+  // final Block1D + 1x1 projection with the ODE update in the epilogue
+  CKR(run_conv_stats(h, pl, R1, R1.hact, C, m.final_conv, site, s));
+  CKR(run_gn_apply(h, R1, m.final_gn, pl->stats + (long long)site * pl->B * 16, nullptr, nullptr, nullptr, R1.sin_, C, s));
+  site++;
+  {
+    GemmParams p = gemm_base(R1.M, R1.sin_, C, R1.M, m.final_proj, nullptr, nullptr);
+    p.mode = EPI_ODE, p.row_info = R1.info;
+    p.c_v = st.c_v;
+    p.ld_k = F;
+    for (int j = 0; j < 3; ++j) {
+      p.c_k[j] = st.c_k[j];
+      p.kin[j] = st.kin[j] >= 0 ? pl->kbuf[st.kin[j]] : nullptr;
+    }
+    p.kout = st.kout >= 0 ? pl->kbuf[st.kout] : nullptr;
+    if (out_f32_override) {  // bare estimator call: v itself
+      p.resid = nullptr, p.out_f32 = out_f32_override, p.ld_f32 = F, p.out_act = nullptr;
+    } else {
+      p.resid = pl->xstate, p.ld_resid = F;
+      p.out_f32 = st.write_state ? pl->xstate : nullptr, p.ld_f32 = F;
+      p.out_act = pl->xin, p.ld_act = pl->xin_ld;
+    }
+    CKR(launch_gemm(h, p, true, s));
+  }
+  return 0;
+}
+
+// Time-embedding MLP for all NFE time points + the per-resnet projections (reference decoder.py:368-369, :51).
+int emit_time_embedding(cfm_handle* h, Plan* pl, int n_t, const float* t_dev, cudaStream_t s) {
+  const int C = h->C(), T4 = 4 * C, IC = h->cfg.in_channels;
+  const Model& m = h->model;
+  auto gemv = [&](const float* x, long long ldx, const float* W, int N, int K, const float* b, int ai, int ao, float* y,
+                  long long ldy) -> int {
+    h->launch_counter++;
+    const long long warps = (long long)n_t * N;
+    gemv_rows_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, s>>>(x, ldx, n_t, W, N, K, b, ai, ao, y, ldy);
+    CK(cudaGetLastError());
+    return 0;
+  };
+  h->launch_counter++;
+  sinusoid_kernel<<<n_t, roundup(IC / 2, 32), 0, s>>>(t_dev, n_t, IC, pl->sinemb);
+  CK(cudaGetLastError());
+  CKR(gemv(pl->sinemb, IC, m.t1_w, T4, IC, m.t1_b, ACT_NONE, ACT_SILU, pl->temb_a, T4));
+  CKR(gemv(pl->temb_a, T4, m.t2_w, T4, T4, m.t2_b, ACT_NONE, ACT_NONE, pl->temb, T4));
+  const int n_res = (int)m.stages.size();
+  for (int r = 0; r < n_res; ++r)
+    CKR(gemv(pl->temb, T4, m.stages[r].res.mlp_w, C, T4, m.stages[r].res.mlp_b, ACT_MISH, ACT_NONE, pl->tproj + (long long)r * C,
+             (long long)n_res * C));
+  return 0;
+}
+
+int emit_pack(cfm_handle* h, Plan* pl, const float* x, const float* mu, cudaStream_t s) {
+  const int F = h->cfg.out_channels;
+  int max_rows = 0;
+  for (int L : pl->L) max_rows = std::max(max_rows, 2 * ((L + 1) / 2 + 2));
+  dim3 grid((max_rows + 31) / 32, (F + 31) / 32, pl->B), block(32, 8);
+  h->launch_counter += 2;
+  if (h->bf) {
+    pack_rows_kernel<bf16><<<grid, block, 0, s>>>(x, F, pl->T, pl->utt1, static_cast<bf16*>(pl->xin), pl->xin_ld, 0, pl->xstate, F, 1.f);
+    pack_rows_kernel<bf16><<<grid, block, 0, s>>>(mu, F, pl->T, pl->utt1, static_cast<bf16*>(pl->xin), pl->xin_ld, F, nullptr, 0, 1.f);
+  } else {
+    pack_rows_kernel<float><<<grid, block, 0, s>>>(x, F, pl->T, pl->utt1, static_cast<float*>(pl->xin), pl->xin_ld, 0, pl->xstate, F, 1.f);
+    pack_rows_kernel<float><<<grid, block, 0, s>>>(mu, F, pl->T, pl->utt1, static_cast<float*>(pl->xin), pl->xin_ld, F, nullptr, 0, 1.f);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int emit_unpack(cfm_handle* h, Plan* pl, const float* state, const float* fill, float* out, cudaStream_t s) {
+  const int F = h->cfg.out_channels;
+  dim3 grid((pl->T + 31) / 32, (F + 31) / 32, pl->B), block(32, 8);
+  h->launch_counter++;
+  unpack_rows_kernel<<<grid, block, 0, s>>>(state, F, pl->utt1, F, pl->T, fill, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int emit_ode_loop(cfm_handle* h, Plan* pl, cudaStream_t s) {
+  CKR(emit_time_embedding(h, pl, (int)pl->stages.size(), pl->tvals, s));
+  for (size_t j = 0; j < pl->stages.size(); ++j) CKR(emit_nfe(h, pl, (int)j, pl->stages[j], nullptr, s));
+  return 0;
+}
+
+int build_stages(cfm_handle* h, Plan* pl, const float* t_span, int n_points, int solver) {
+  pl->stages.clear();
+  for (int i = 0; i + 1 < n_points; ++i) {
+    const float t0 = t_span[i], t1 = t_span[i + 1];
+    const float dt = t1 - t0;
+    auto mk = [&](float t, float cv) {
+      OdeStage st;
+      st.t = t, st.c_v = cv, st.kout = -1, st.write_state = false;
+      for (int j = 0; j < 3; ++j) st.c_k[j] = 0.f, st.kin[j] = -1;
+      return st;
+    };
+    if (solver == CFM_SOLVER_EULER) {
+      OdeStage a = mk(t0, dt);
+      a.write_state = true;
+      pl->stages.push_back(a);
+    } else if (solver == CFM_SOLVER_MIDPOINT) {
+      const float half = 0.5f * dt;
+      pl->stages.push_back(mk(t0, half));
+      OdeStage b = mk(t0 + half, dt);
+      b.write_state = true;
+      pl->stages.push_back(b);
+    } else if (solver == CFM_SOLVER_HEUN3) {
+      OdeStage a = mk(t0, dt / 3.f);
+      a.kout = 0;
+      OdeStage b = mk(t0 + dt / 3.f, dt * 2.f / 3.f);
+      OdeStage c = mk(t0 + dt * 2.f / 3.f, dt * 0.75f);
+      c.kin[0] = 0, c.c_k[0] = dt * 0.25f, c.write_state = true;
+      pl->stages.push_back(a), pl->stages.push_back(b), pl->stages.push_back(c);
+    } else if (solver == CFM_SOLVER_RK4) {  // torchdiffeq's 3/8-rule
+      OdeStage a = mk(t0, dt / 3.f);
+      a.kout = 0;
+      OdeStage b = mk(t0 + dt / 3.f, dt);
+      b.kin[0] = 0, b.c_k[0] = -dt / 3.f, b.kout = 1;
+      OdeStage c = mk(t0 + dt * 2.f / 3.f, dt);
+      c.kin[0] = 0, c.c_k[0] = dt, c.kin[1] = 1, c.c_k[1] = -dt, c.kout = 2;
+      OdeStage d = mk(t1, dt * 0.125f);
+      d.kin[0] = 0, d.c_k[0] = dt * 0.125f, d.kin[1] = 1, d.c_k[1] = dt * 0.375f, d.kin[2] = 2, d.c_k[2] = dt * 0.375f;
+      d.write_state = true;
+      pl->stages.push_back(a), pl->stages.push_back(b), pl->stages.push_back(c), pl->stages.push_back(d);
+    } else {
+      return fail(h, CFM_ERR_INVALID, "unknown solver id %d (expected euler=0, midpoint=1, heun3=2, rk4=3)", solver);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* cfm_last_error(const cfm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cfm_create(const cfm_config* cfg, cfm_handle** out) {
+  cfm_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, CFM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->channels <= 0 || cfg->channels % 64 != 0 || cfg->channels > 512)
+    return fail(h, CFM_ERR_INVALID, "channels must be a multiple of 64 in [64, 512], got %d", cfg->channels);
+  if (cfg->head_dim != 64 && cfg->head_dim != 32) return fail(h, CFM_ERR_INVALID, "head_dim must be 64 or 32, got %d", cfg->head_dim);
+  if (cfg->n_heads <= 0 || cfg->n_blocks < 1 || cfg->n_mid_blocks < 1 || cfg->out_channels <= 0 ||
+      cfg->in_channels < 2 * cfg->out_channels || cfg->in_channels % 2 != 0)
+    return fail(h, CFM_ERR_INVALID, "invalid estimator configuration");
+  if ((cfg->n_heads * cfg->head_dim) % 64 != 0) return fail(h, CFM_ERR_INVALID, "heads*head_dim must be a multiple of 64");
+  if (cfg->out_channels % 4 != 0) return fail(h, CFM_ERR_INVALID, "out_channels must be a multiple of 4");
+  if (cfg->precision != CFM_PREC_BF16 && cfg->precision != CFM_PREC_FP32) return fail(h, CFM_ERR_INVALID, "unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, CFM_ERR_CUDA, "no CUDA device: libcfm_b200 has no CPU path");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, CFM_ERR_INVALID, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(h, CFM_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(h, CFM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major,
+                prop.minor);
+  h = new cfm_handle();
+  h->cfg = *cfg;
+  h->bf = cfg->precision == CFM_PREC_BF16;
+  h->es = h->bf ? 2 : 4;
+  h->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    delete h;
+    return code;
+  };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(CFM_ERR_CUDA); }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    h->err = "cuTensorMapEncodeTiled not available from the driver";
+    return bail(CFM_ERR_CUDA);
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int r = 0;
+  r = r ? r : set_tc_attr<64>(h);
+  r = r ? r : set_tc_attr<128>(h);
+  r = r ? r : set_tc_attr<160>(h);
+  r = r ? r : set_tc_attr<192>(h);
+  r = r ? r : set_tc_attr<256>(h);
+  r = r ? r : attn_tc_set_attr(&h->err);
+  if (r) return bail(r);
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }
+  *out = h;
+  return 0;
+}
+
+void cfm_destroy(cfm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  free_plan(h);
+  free_arena(h->wallocs);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int cfm_load_weights(cfm_handle* h, const cfm_weight_desc* descs, int32_t n) {
+  if (!h || !descs || n <= 0) return fail(h, CFM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  free_plan(h);  // the captured graph references the old weight buffers
+  free_arena(h->wallocs);
+  h->model = Model();
+  h->weights_loaded = false;
+  DescMap dm;
+  for (int i = 0; i < n; ++i) {
+    if (!descs[i].name) return fail(h, CFM_ERR_WEIGHTS, "descriptor %d has no name", i);
+    dm.by_name[descs[i].name] = &descs[i];
+    dm.used[descs[i].name] = false;
+  }
+  const int C = h->C(), T4 = 4 * C, IC = h->cfg.in_channels, F = h->cfg.out_channels;
+  Model& m = h->model;
+  const float* p;
+  CKR(want(h, dm, "time_mlp.linear_1.weight", {T4, IC}, &p));
+  CKR(copy_f32(h, p, (size_t)T4 * IC, &m.t1_w));
+  CKR(want(h, dm, "time_mlp.linear_1.bias", {T4}, &p));
+  CKR(copy_f32(h, p, T4, &m.t1_b));
+  CKR(want(h, dm, "time_mlp.linear_2.weight", {T4, T4}, &p));
+  CKR(copy_f32(h, p, (size_t)T4 * T4, &m.t2_w));
+  CKR(want(h, dm, "time_mlp.linear_2.bias", {T4}, &p));
+  CKR(copy_f32(h, p, T4, &m.t2_b));
+  m.stages.resize(4 + h->cfg.n_mid_blocks);
+  int si = 0;
+  CKR(load_stage(h, dm, "down_blocks.0", IC, m.stages[si++]));
+  CKR(load_stage(h, dm, "down_blocks.1", C, m.stages[si++]));
+  for (int i = 0; i < h->cfg.n_mid_blocks; ++i) CKR(load_stage(h, dm, "mid_blocks." + std::to_string(i), C, m.stages[si++]));
+  CKR(load_stage(h, dm, "up_blocks.0", 2 * C, m.stages[si++]));
+  CKR(load_stage(h, dm, "up_blocks.1", 2 * C, m.stages[si++]));
+  CKR(load_conv(h, dm, "down_blocks.0.2.conv", C, C, 3, m.down_s2));
+  CKR(load_conv(h, dm, "down_blocks.1.2", C, C, 3, m.down_tail));
+  {  // ConvTranspose1d weight [Cin, Cout, 4]: out[2i] = W1 x[i] + W3 x[i-1];  out[2i+1] = W2 x[i] + W0 x[i+1]
+    const float *w, *b;
+    CKR(want(h, dm, "up_blocks.0.2.conv.weight", {C, C, 4}, &w));
+    CKR(want(h, dm, "up_blocks.0.2.conv.bias", {C}, &b));
+    CKR(alloc_gemm(h, m.up_even, C, C, 2));
+    CKR(pack_into(h, m.up_even, w, 4, (long long)C * 4, 1, make_int4(3, 1, 0, 0), C, 0));
+    CKR(copy_f32(h, b, C, &m.up_even.bias));
+    CKR(alloc_gemm(h, m.up_odd, C, C, 2));
+    CKR(pack_into(h, m.up_odd, w, 4, (long long)C * 4, 1, make_int4(2, 0, 0, 0), C, 0));
+    CKR(copy_f32(h, b, C, &m.up_odd.bias));
+  }
+  CKR(load_conv(h, dm, "up_blocks.1.2", C, C, 3, m.up_tail));
+  CKR(load_conv(h, dm, "final_block.block.0", C, C, 3, m.final_conv));
+  CKR(load_norm(h, dm, "final_block.block.1", C, m.final_gn, m.final_conv.bias));
+  CKR(load_conv(h, dm, "final_proj", F, C, 1, m.final_proj));
+  for (auto& kv : dm.used)
+    if (!kv.second) return fail(h, CFM_ERR_WEIGHTS, "unexpected parameter '%s'", kv.first.c_str());
+  CK(cudaDeviceSynchronize());
+  h->weights_loaded = true;
+  return 0;
+}
+
+int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad, const float* t_span, int32_t n_points,
+             int32_t solver) {
+  if (!h || !lengths || !t_span) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->weights_loaded) return fail(h, CFM_ERR_STATE, "cfm_plan before cfm_load_weights");
+  if (batch <= 0 || batch >= (1 << 24)) return fail(h, CFM_ERR_INVALID, "batch out of range");
+  if (t_pad <= 0 || (t_pad & 1)) return fail(h, CFM_ERR_INVALID, "t_pad must be positive and even (reference fix_len_compatibility), got %d", t_pad);
+  if (n_points < 2) return fail(h, CFM_ERR_INVALID, "t_span needs at least 2 points");
+  for (int b = 0; b < batch; ++b)
+    if (lengths[b] < 1 || lengths[b] > t_pad) return fail(h, CFM_ERR_INVALID, "lengths[%d]=%d outside [1, t_pad=%d]", b, lengths[b], t_pad);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  free_plan(h);
+  Plan* pl = new Plan();
+  h->plan = pl;
+  pl->B = batch, pl->T = t_pad;
+  pl->L.assign(lengths, lengths + batch);
+  CKR(build_stages(h, pl, t_span, n_points, solver));
+
+  // ---- packed row tables (DESIGN.md "data layout"): a half-res segment is L2 valid rows + the halo / pad-token row +
+  // one zero guard row (the halo row's k=3 conv reads row L2+1, which must not be the next utterance); full-res = 2x that.
+  std::vector<UttTable> u1(batch), u2(batch);
+  int s2 = 0;
+  for (int b = 0; b < batch; ++b) {
+    const int L = lengths[b], P = t_pad - L, L2 = (L + 1) / 2, T2 = t_pad / 2, P2 = T2 - L2;
+    u2[b].start = s2, u2[b].len = L2, u2[b].rows = L2 + 2, u2[b].bias_rows = std::max(P2 - 1, 0), u2[b].t_res = T2;
+    u2[b].pad_key_bias = P2 >= 1 ? logf((float)P2) - 1.f : -INFINITY;
+    u1[b].start = 2 * s2, u1[b].len = L, u1[b].rows = 2 * (L2 + 2), u1[b].bias_rows = std::max(P - 1, 0), u1[b].t_res = t_pad;
+    u1[b].pad_key_bias = P >= 1 ? logf((float)P) - 1.f : -INFINITY;
+    s2 += L2 + 2;
+  }
+  pl->M2 = s2, pl->M1 = 2 * s2;
+  std::vector<int> i1(pl->M1, 0), i2(pl->M2, 0);
+  std::vector<int4> w1, w2;
+  const int QT = 128;
+  for (int b = 0; b < batch; ++b) {
+    for (int r = 0; r < 2; ++r) {
+      const UttTable& u = r == 0 ? u1[b] : u2[b];
+      std::vector<int>& info = r == 0 ? i1 : i2;
+      const int P = u.t_res - u.len;
+      for (int t = 0; t < u.rows; ++t) {
+        int v = b;
+        if (t < u.len) v |= ROW_VALID | ROW_INSTAT;
+        else if (t == u.len && P >= 1) v |= ROW_INSTAT;
+        info[u.start + t] = v;
+      }
+      std::vector<int4>& w = r == 0 ? w1 : w2;
+      for (int hd = 0; hd < h->cfg.n_heads; ++hd)
+        for (int q0 = 0; q0 < u.len + 1; q0 += QT) w.push_back(make_int4(b, hd, q0, 0));
+    }
+  }
+  pl->n_work1 = (int)w1.size(), pl->n_work2 = (int)w2.size();
+  auto up = [&](auto** dst, const auto& vec) -> int {
+    using E = typename std::remove_reference<decltype(vec[0])>::type;
+    CKR(dev_alloc(h, pl->allocs, reinterpret_cast<void**>(dst), vec.size() * sizeof(E), &pl->bytes));
+    CK(cudaMemcpy(*dst, vec.data(), vec.size() * sizeof(E), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  CKR(up(&pl->utt1, u1));
+  CKR(up(&pl->utt2, u2));
+  CKR(up(&pl->info1, i1));
+  CKR(up(&pl->info2, i2));
+  CKR(up(&pl->work1, w1));
+  CKR(up(&pl->work2, w2));
+
+  // ---- workspace
+  const int C = h->C(), I = h->inner(), F = h->cfg.out_channels, es = h->es, T4 = 4 * C;
+  const int n_t = (int)pl->stages.size(), n_res = 4 + h->cfg.n_mid_blocks;
+  std::vector<float> tv(n_t);
+  for (int j = 0; j < n_t; ++j) tv[j] = pl->stages[j].t;
+  CKR(up(&pl->tvals, tv));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->sinemb, (size_t)n_t * h->cfg.in_channels, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->temb_a, (size_t)n_t * T4, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->temb, (size_t)n_t * T4, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->tproj, (size_t)n_t * n_res * C, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->xstate, (size_t)pl->M1 * F, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->vout, (size_t)pl->M1 * F, &pl->bytes));
+  int n_k = 0;
+  for (auto& st : pl->stages) n_k = std::max(n_k, st.kout + 1);
+  for (int j = 0; j < n_k; ++j) CKR(dev_alloc_t(h, pl->allocs, &pl->kbuf[j], (size_t)pl->M1 * F, &pl->bytes));
+  const int n_sites = 2 * n_res + 1;
+  pl->stats_bytes = (size_t)n_sites * batch * 16 * sizeof(double);
+  CKR(dev_alloc(h, pl->allocs, reinterpret_cast<void**>(&pl->stats), pl->stats_bytes, &pl->bytes));
+  pl->xin_ld = roundup(h->cfg.in_channels, 64);
+  CKR(dev_alloc(h, pl->allocs, &pl->xin, (size_t)pl->M1 * pl->xin_ld * es, &pl->bytes));
+  for (int r = 0; r < 2; ++r) {
+    const size_t M = r == 0 ? pl->M1 : pl->M2;
+    CKR(dev_alloc_t(h, pl->allocs, &pl->hraw[r], M * C, &pl->bytes));
+    CKR(dev_alloc_t(h, pl->allocs, &pl->rres[r], M * C, &pl->bytes));
+    CKR(dev_alloc_t(h, pl->allocs, &pl->X[r], M * C, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->hact[r], M * C * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->Xn[r], M * C * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->qkv[r], M * 3 * I * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->ao[r], M * I * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->ffh[r], M * 4 * C * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->sin_[r], M * C * es, &pl->bytes));
+    CKR(dev_alloc(h, pl->allocs, &pl->cat[r], M * 2 * C * es, &pl->bytes));
+  }
+  CK(cudaDeviceSynchronize());
+
+  // ---- capture the whole ODE loop as one CUDA graph
+  h->launch_counter = 0;
+  if (!(h->cfg.flags & CFM_FLAG_NO_GRAPH)) {
+    CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    int r = emit_ode_loop(h, pl, h->own_stream);
+    cudaError_t e = cudaStreamEndCapture(h->own_stream, &pl->graph);
+    if (r) return r;
+    if (e != cudaSuccess) return fail(h, CFM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+    pl->launches_per_solve = h->launch_counter + 3;  // + pack x, pack mu, unpack
+  }
+  return 0;
+}
+
+int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* stream) {
+  if (!h || !mu || !z || !out) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_solve before cfm_plan");
+  Plan* pl = h->plan;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(h->cfg.device));
+  h->launch_counter = 0;
+  CKR(emit_pack(h, pl, z, mu, s));
+  if (pl->exec) {
+    CK(cudaGraphLaunch(pl->exec, s));
+  } else {
+    CKR(emit_ode_loop(h, pl, s));
+    pl->launches_per_solve = h->launch_counter + 1;
+  }
+  CKR(emit_unpack(h, pl, pl->xstate, z, out, s));
+  return 0;
+}
+
+int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) {
+  if (!h || !mu || !z || !out) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_solve_host before cfm_plan");
+  Plan* pl = h->plan;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)pl->B * h->cfg.out_channels * pl->T;
+  float *dmu = nullptr, *dz = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&dmu, n * 4));
+  CK(cudaMalloc(&dz, n * 4));
+  CK(cudaMalloc(&dout, n * 4));
+  int r = 0;
+  cudaError_t e = cudaMemcpyAsync(dmu, mu, n * 4, cudaMemcpyHostToDevice, h->own_stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dz, z, n * 4, cudaMemcpyHostToDevice, h->own_stream);
+  if (e == cudaSuccess) r = cfm_solve(h, dmu, dz, dout, h->own_stream);
+  if (e == cudaSuccess && r == 0) e = cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, h->own_stream);
+  if (e == cudaSuccess && r == 0) e = cudaStreamSynchronize(h->own_stream);
+  cudaFree(dmu), cudaFree(dz), cudaFree(dout);
+  if (r) return r;
+  if (e != cudaSuccess) return fail(h, CFM_ERR_CUDA, "cfm_solve_host: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream) {
+  if (!h || !x || !mu || !v) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_estimator before cfm_plan");
+  Plan* pl = h->plan;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(h->cfg.device));
+  CKR(emit_pack(h, pl, x, mu, s));
+  CK(cudaMemcpyAsync(pl->tvals, &t, sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // `t` lives on this call's stack
+  CKR(emit_time_embedding(h, pl, 1, pl->tvals, s));
+  OdeStage st;
+  st.t = t, st.c_v = 1.f, st.kout = -1, st.write_state = false;
+  for (int j = 0; j < 3; ++j) st.c_k[j] = 0.f, st.kin[j] = -1;
+  h->launch_counter = 0;
+  CKR(emit_nfe(h, pl, 0, st, pl->vout, s));
+  CKR(emit_unpack(h, pl, pl->vout, nullptr, v, s));
+  // restore the planned time grid for subsequent solves
+  std::vector<float> tv(pl->stages.size());
+  for (size_t j = 0; j < tv.size(); ++j) tv[j] = pl->stages[j].t;
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(pl->tvals, tv.data(), tv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int cfm_plan_info(const cfm_handle* h, int64_t* rows_full, int64_t* rows_half, int64_t* n_nfe, int64_t* kernels_per_solve,
+                  int64_t* workspace_bytes) {
+  if (!h || !h->plan) return CFM_ERR_STATE;
+  if (rows_full) *rows_full = h->plan->M1;
+  if (rows_half) *rows_half = h->plan->M2;
+  if (n_nfe) *n_nfe = (int64_t)h->plan->stages.size();
+  if (kernels_per_solve) *kernels_per_solve = h->plan->launches_per_solve;
+  if (workspace_bytes) *workspace_bytes = (int64_t)h->plan->bytes;
+  return 0;
+}
+
+int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max_elems, int64_t* rows, int64_t* cols) {
+  if (!h || !h->plan || !name) return fail(h, CFM_ERR_STATE, "cfm_debug_read needs a plan");
+  Plan* pl = h->plan;
+  const int C = h->C(), I = h->inner(), F = h->cfg.out_channels;
+  struct Ent { const char* n; const void* p; long long r, c; bool act; };
+  const Ent table[] = {
+      {"xin", pl->xin, pl->M1, pl->xin_ld, true},   {"xstate", pl->xstate, pl->M1, F, false},
+      {"vout", pl->vout, pl->M1, F, false},         {"hraw1", pl->hraw[0], pl->M1, C, false},
+      {"hraw2", pl->hraw[1], pl->M2, C, false},     {"rres1", pl->rres[0], pl->M1, C, false},
+      {"X1", pl->X[0], pl->M1, C, false},           {"X2", pl->X[1], pl->M2, C, false},
+      {"hact1", pl->hact[0], pl->M1, C, true},      {"hact2", pl->hact[1], pl->M2, C, true},
+      {"Xn1", pl->Xn[0], pl->M1, C, true},          {"qkv1", pl->qkv[0], pl->M1, 3 * I, true},
+      {"qkv2", pl->qkv[1], pl->M2, 3 * I, true},    {"ao1", pl->ao[0], pl->M1, I, true},
+      {"ao2", pl->ao[1], pl->M2, I, true},          {"ffh1", pl->ffh[0], pl->M1, 4 * C, true},
+      {"sin1", pl->sin_[0], pl->M1, C, true},       {"sin2", pl->sin_[1], pl->M2, C, true},
+      {"cat1", pl->cat[0], pl->M1, 2 * C, true},    {"cat2", pl->cat[1], pl->M2, 2 * C, true},
+      {"sinemb", pl->sinemb, (long long)pl->stages.size(), h->cfg.in_channels, false},
+      {"temb", pl->temb, (long long)pl->stages.size(), 4 * C, false},
+      {"tproj", pl->tproj, (long long)pl->stages.size(), (4 + h->cfg.n_mid_blocks) * C, false},
+  };
+  for (const Ent& e : table) {
+    if (strcmp(e.n, name) != 0) continue;
+    const long long n = e.r * e.c;
+    if (rows) *rows = e.r;
+    if (cols) *cols = e.c;
+    if (!host_dst) return 0;
+    if (n > max_elems) return fail(h, CFM_ERR_INVALID, "buffer '%s' needs %lld elements", name, n);
+    CK(cudaDeviceSynchronize());
+    if (!e.act || !h->bf) {
+      CK(cudaMemcpy(host_dst, e.p, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<uint16_t> tmp(n);
+      CK(cudaMemcpy(tmp.data(), e.p, n * 2, cudaMemcpyDeviceToHost));
+      for (long long i = 0; i < n; ++i) {
+        uint32_t u = (uint32_t)tmp[i] << 16;
+        memcpy(&host_dst[i], &u, 4);
+      }
+    }
+    return 0;
+  }
+  if (strcmp(name, "stats") == 0) {  // [sites][B][8][2] doubles, returned as fp32
+    const long long n = (long long)(pl->stats_bytes / sizeof(double));
+    if (rows) *rows = n / 16;
+    if (cols) *cols = 16;
+    if (!host_dst) return 0;
+    if (n > max_elems) return fail(h, CFM_ERR_INVALID, "buffer 'stats' needs %lld elements", n);
+    CK(cudaDeviceSynchronize());
+    std::vector<double> tmp(n);
+    CK(cudaMemcpy(tmp.data(), pl->stats, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; ++i) host_dst[i] = (float)tmp[i];
+    return 0;
+  }
+  return fail(h, CFM_ERR_INVALID, "unknown debug buffer '%s'", name);
+}
+
+int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches) {
+  if (!h) return CFM_ERR_INVALID;
+  h->stop_after = n_launches;
+  return 0;
+}
+
+int cfm_debug_gemm(cfm_handle* h, const void* a, const void* w, float* d, int32_t M, int32_t N, int32_t K, int32_t n_taps,
+                   const int32_t* shifts, int32_t use_tc, void* stream) {
+  if (!h || !a || !w || !d) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->bf) return fail(h, CFM_ERR_INVALID, "cfm_debug_gemm needs a bf16 handle");
+  if (n_taps < 1 || n_taps > MAX_TAPS) return fail(h, CFM_ERR_INVALID, "n_taps out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  GemmW gw;
+  gw.w = const_cast<void*>(w), gw.N = N, gw.K = K, gw.Kp = K, gw.n_taps = n_taps, gw.n_stride = N;
+  GemmParams p = gemm_base(M, a, K, M, gw, shifts, nullptr);
+  p.mode = EPI_STATS, p.fused_stats = 0, p.out_f32 = d, p.ld_f32 = N;
+  const int saved = h->cfg.flags;
+  if (!use_tc) h->cfg.flags |= CFM_FLAG_SIMT_GEMM; else h->cfg.flags &= ~CFM_FLAG_SIMT_GEMM;
+  int r = launch_gemm(h, p, true, static_cast<cudaStream_t>(stream));
+  h->cfg.flags = saved;
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// Bandwidth-side kernels of the estimator: pack / unpack between the caller's (B, F, T) tensors and the
+// token-major packed layout, GroupNorm statistics + apply (+Mish, mask, time-embedding / residual add),
+// LayerNorm, the time-embedding MLP, weight packing.  fp32 math everywhere; `T` is the activation storage
+// type (bf16 in the tensor-core mode, float in the fp32 mode).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "gemm.cuh"
+
+namespace cfm {
+
+struct UttTable {        // one entry per utterance and resolution
+  int start;             // first packed row
+  int len;               // valid frames L
+  int rows;              // rows owned in the packed buffer
+  int bias_rows;         // max(P - 1, 0): padded frames whose conv output is exactly the bias
+  int t_res;             // padded length T at this resolution (GroupNorm denominator)
+  float pad_key_bias;    // log(P) - 1 for the virtual pad token's key, -inf when P == 0
+};
+
+__device__ __forceinline__ float mish_f(float x) {
+  // x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)     (reference decoder.py:40 nn.Mish)
+  if (x > 20.f) return x;
+  float e = __expf(x);
+  float n = e * (e + 2.f);
+  return x * __fdividef(n, n + 2.f);
+}
+__device__ __forceinline__ float mish_precise(float x) {
+  if (x > 20.f) return x;
+  float e = expf(x);
+  float n = e * (e + 2.f);
+  return x * (n / (n + 2.f));
+}
+
+// ---------------------------------------------------------------------------------- pack / unpack
+// (B, F, T) fp32 channels-first  ->  rows [start_b + t], columns [col0, col0 + F) of a token-major buffer.
+// Rows t >= L of the utterance's segment are written as zero.  Optionally also writes the fp32 state.
+template <typename T>
+__global__ void pack_rows_kernel(const float* __restrict__ src, int F, int Tpad, const UttTable* __restrict__ utt,
+                                 T* __restrict__ dst_act, long long ld_act, int col0, float* __restrict__ dst_f32,
+                                 long long ld_f32, float scale) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const UttTable u = utt[b];
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  if (t0 >= u.rows) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int f = f0 + i, t = t0 + tx;
+    float v = 0.f;
+    if (f < F && t < u.len) v = src[((long long)b * F + f) * Tpad + t] * scale;
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int t = t0 + i, f = f0 + tx;
+    if (t < u.rows && f < F) {
+      float v = tile[tx][i];
+      long long row = u.start + t;
+      if (dst_act) ActIO<T>::st(dst_act + row * ld_act + col0 + f, v);
+      if (dst_f32) dst_f32[row * ld_f32 + f] = v;
+    }
+  }
+}
+
+// token-major fp32 state -> (B, F, T); frames t >= L take `fill` (the injected noise z for a solve, because the
+// masked velocity never moves padded frames; nullptr -> 0 for a bare estimator call).
+__global__ void unpack_rows_kernel(const float* __restrict__ state, long long ld, const UttTable* __restrict__ utt, int F,
+                                   int Tpad, const float* __restrict__ fill, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const UttTable u = utt[b];
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    int t = t0 + i, f = f0 + tx;
+    float v = 0.f;
+    if (t < u.len && f < F) v = state[(long long)(u.start + t) * ld + f];
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int f = f0 + i, t = t0 + tx;
+    if (f < F && t < Tpad) {
+      long long o = ((long long)b * F + f) * Tpad + t;
+      dst[o] = (t < u.len) ? tile[tx][i] : (fill ? fill[o] : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- GroupNorm
+// Stand-alone statistics pass (fp32 mode and the debug path; the tensor-core GEMM fuses this into its epilogue).
+__global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M, int C, int group_ch,
+                                const int* __restrict__ row_info, double* __restrict__ stats) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row, group)
+  const int m = idx >> 3, g = idx & 7;
+  if (m >= M) return;
+  const int info = row_info[m];
+  if (!(info & ROW_INSTAT)) return;
+  const float* p = h + (long long)m * ld + g * group_ch;
+  float s = 0.f, ss = 0.f;
+  for (int i = 0; i < group_ch; ++i) {
+    float v = p[i];
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+  const int utt = info & ROW_UTT_MASK;
+  atomicAdd(stats + ((long long)utt * 8 + g) * 2, (double)s);
+  atomicAdd(stats + ((long long)utt * 8 + g) * 2 + 1, (double)ss);
+}
+
+// y = valid ? Mish(GN(h)) + addvec[c] : 0;  y += resid[m, c];  -> out_f32 and/or out_act.
+// GN statistics = epilogue sums + bias_rows * (sum_c b_c, sum_c b_c^2) for the padded frames that are never
+// materialised (DESIGN.md "pad-aware packing"), over group_ch * t_res elements (reference decoder.py:35-45
+// normalises over the PADDED length).
+template <typename T, bool PRECISE>
+__global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int M, int C, int group_ch,
+                                const int* __restrict__ row_info, const UttTable* __restrict__ utt,
+                                const double* __restrict__ stats, const double* __restrict__ bias_gsum,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ addvec, const float* __restrict__ resid, long long ld_resid,
+                                float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act, long long ld_act) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = C >> 2;
+  const int m = (int)(idx / c4);
+  if (m >= M) return;
+  const int c = (int)(idx % c4) * 4;
+  const int info = row_info[m];
+  const bool valid = (info & ROW_VALID) != 0;
+  float y[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const int b = info & ROW_UTT_MASK;
+    const int g = c / group_ch;
+    const UttTable u = utt[b];
+    const double n = (double)group_ch * (double)u.t_res;
+    const double s = stats[((long long)b * 8 + g) * 2] + (double)u.bias_rows * bias_gsum[g * 2];
+    const double ss = stats[((long long)b * 8 + g) * 2 + 1] + (double)u.bias_rows * bias_gsum[g * 2 + 1];
+    const double mean = s / n;
+    const double var = fmax(ss / n - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float fmean = (float)mean;
+    const float4 hv = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
+    const float4 gv = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 bv = *reinterpret_cast<const float4*>(beta + c);
+    float x[4] = {hv.x, hv.y, hv.z, hv.w};
+    float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float be[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float z = fmaf((x[i] - fmean) * rstd, ga[i], be[i]);
+      y[i] = PRECISE ? mish_precise(z) : mish_f(z);
+      if (addvec) y[i] += __ldg(addvec + c + i);
+    }
+  }
+  if (resid) {
+    const float4 r = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
+    y[0] += r.x, y[1] += r.y, y[2] += r.z, y[3] += r.w;
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+  if (out_act) {
+    T* d = out_act + (long long)m * ld_act + c;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), bb = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&bb);
+      *reinterpret_cast<uint2*>(d) = o;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+  }
+}
+
+// per-GroupNorm-site sums of the conv bias per group: [8][2] doubles (sum b, sum b^2)
+__global__ void bias_group_sums_kernel(const float* __restrict__ bias, int C, int group_ch, double* __restrict__ out) {
+  const int g = threadIdx.x;
+  if (g >= 8) return;
+  double s = 0, ss = 0;
+  for (int i = 0; i < group_ch; ++i) {
+    double b = bias[g * group_ch + i];
+    s += b;
+    ss += b * b;
+  }
+  out[g * 2] = s;
+  out[g * 2 + 1] = ss;
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm
+// One warp per row, C <= 32 * MAXV.  eps = 1e-5, biased variance (torch.nn.LayerNorm; reference transformer.py:179,215).
+template <typename T, int MAXV>
+__global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, int M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, T* __restrict__ out, long long ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* xr = x + (long long)warp * ldx;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    v[i] = (c < C) ? xr[c] : 0.f;
+    s += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    float d = (c < C) ? v[i] - mean : 0.f;
+    ss = fmaf(d, d, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+  T* orow = out + (long long)warp * ldo;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + 32 * i;
+    if (c < C) ActIO<T>::st(orow + c, fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+  }
+}
+
+// ---------------------------------------------------------------------------------- time embedding
+// Sinusoidal features (reference decoder.py:20-29) for NT time points: [NT][dim] = [sin | cos](1000 t f_k),
+// f_k = exp(-k ln(1e4)/(half-1)).  The reference evaluates this in fp32; each fp32 rounding step is reproduced,
+// with the transcendental functions taken in double and rounded once.
+__global__ void sinusoid_kernel(const float* __restrict__ t, int NT, int dim, float* __restrict__ out) {
+  const int i = blockIdx.x, k = threadIdx.x;
+  const int half = dim / 2;
+  if (i >= NT || k >= half) return;
+  const float step = (float)(-(log(10000.0) / (double)(half - 1)));
+  const float prod = (float)k * step;
+  const float freq = (float)exp((double)prod);
+  const float a = 1000.f * t[i];
+  const float arg = a * freq;
+  out[(long long)i * dim + k] = (float)sin((double)arg);
+  out[(long long)i * dim + half + k] = (float)cos((double)arg);
+}
+
+enum GemvAct : int { ACT_NONE = 0, ACT_SILU = 1, ACT_MISH = 2 };
+// y[i][n] = act_out(bias[n] + sum_k W[n][k] * act_in(x[i][k]));  one warp per (i, n); fp32 weights.
+__global__ void gemv_rows_kernel(const float* __restrict__ x, long long ldx, int NT, const float* __restrict__ W, int N,
+                                 int K, const float* __restrict__ bias, int act_in, int act_out, float* __restrict__ y,
+                                 long long ldy) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= NT * N) return;
+  const int i = gw / N, n = gw % N;
+  const float* xr = x + (long long)i * ldx;
+  const float* wr = W + (long long)n * K;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = xr[k];
+    if (act_in == ACT_MISH) xv = mish_precise(xv);
+    s = fmaf(wr[k], xv, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    s += bias[n];
+    if (act_out == ACT_SILU) s = s / (1.f + expf(-s));
+    y[(long long)i * ldy + n] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// dst[(tap * n_stride + n) * ldd + k] = src[n * s_n + k * s_k + tap_k[tap] * s_t], zero for k in [K, ldd).
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, long long s_n, long long s_k, long long s_t, int n_taps,
+                                   int4 tap_k, int N, int K, T* __restrict__ dst, long long ldd, int n_stride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_tap = (long long)N * ldd;
+  if (idx >= per_tap * n_taps) return;
+  const int tap = (int)(idx / per_tap);
+  const long long rem = idx % per_tap;
+  const int n = (int)(rem / ldd), k = (int)(rem % ldd);
+  const int tk = tap == 0 ? tap_k.x : tap == 1 ? tap_k.y : tap == 2 ? tap_k.z : tap_k.w;
+  float v = (k < K) ? src[n * s_n + k * s_k + tk * s_t] : 0.f;
+  ActIO<T>::st(dst + ((long long)tap * n_stride + n) * ldd + k, v);
+}
+
+__global__ void snake_consts_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, int N,
+                                    float* __restrict__ ea, float* __restrict__ ib) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  ea[i] = expf(alpha[i]);
+  ib[i] = 1.0f / (expf(beta[i]) + 1e-9f);  // reference transformer.py:59,75
+}
+
+}  // namespace cfm

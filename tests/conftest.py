@@ -45,5 +45,5 @@ def cfm_params(solver="euler"):
 
 
 def rel_l2(a, b):
-    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))

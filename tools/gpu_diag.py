@@ -1,0 +1,307 @@
+"""GPU bring-up diagnostics: runs each check in its own subprocess (timeout-guarded) so one fault or hang does not
+hide the rest.  Usage on the GPU box:  python tools/gpu_diag.py [check ...]   -> gpurun_out/diag.log"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _models(dec, solver, precision, flags, seed=1234):
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    from oracle import cfm_oracle as O
+    cp = types.SimpleNamespace(solver=solver, sigma_min=1e-4, use_mu_prior=True)
+    ora = O.CFM(200, 100, cp, dec).eval()
+    P.synthetic.fill_named_seed(ora.estimator, seed)
+    m = P.CFM(200, 100, cp, dec, precision=precision, flags=flags).eval()
+    m.estimator.load_state_dict(ora.estimator.state_dict())
+    return ora, m.cuda()
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+TINY = dict(channels=(64, 64), dropout=0.05, attention_head_dim=32, n_blocks=2, num_mid_blocks=2, num_heads=2)
+TINY64 = dict(channels=(128, 128), dropout=0.05, attention_head_dim=64, n_blocks=1, num_mid_blocks=1, num_heads=2)
+
+
+def check_estimator(precision, flags, dec=TINY, lengths=(40, 33, 17), T=40, label=""):
+    import torch
+    import matcha_tts_24k_b200 as P
+    ora, m = _models(dec, "euler", precision, flags)
+    mu, mask, z, _ = P.synthetic.make_inputs(list(lengths), seed=7, T=T)
+    with torch.inference_mode():
+        v_ref = ora.estimator(z, mask, mu, torch.tensor(0.3))
+    v = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), torch.tensor(0.3))
+    torch.cuda.synchronize()
+    print(f"[estimator {label} prec={precision} flags={flags}] rel_l2={rel(v, v_ref):.3e} max_abs={float((v.cpu()-v_ref).abs().max()):.3e}"
+          f" finite={bool(torch.isfinite(v).all())}")
+    return m, ora
+
+
+def check_solve(precision, flags, dec=TINY, lengths=(40, 33, 17), T=40, solver="euler", n=3, label=""):
+    import torch
+    import matcha_tts_24k_b200 as P
+    ora, m = _models(dec, solver, precision, flags)
+    mu, mask, z, _ = P.synthetic.make_inputs(list(lengths), seed=7, T=T)
+    ts = torch.linspace(0, 1, n + 1)
+    ref = ora.solve(z, ts, mu, mask)
+    out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    print(f"[solve {label} {solver}/{n} prec={precision} flags={flags}] rel_l2={rel(out, ref):.3e} "
+          f"max_abs={float((out.cpu()-ref).abs().max()):.3e} info={m.plan_info()}")
+
+
+def c_fp32_simt():
+    check_estimator("fp32", 1, label="tiny")
+    check_estimator("fp32", 1, lengths=(9, 30, 1, 2), T=64, label="tiny-padded")
+    check_solve("fp32", 1, label="tiny")
+    check_solve("fp32", 0, label="tiny-graph")
+    check_solve("fp32", 0, solver="midpoint", n=2, lengths=(21, 38), T=38, label="tiny")
+    check_solve("fp32", 0, solver="rk4", n=1, lengths=(9, 14), T=20, label="tiny")
+    check_solve("fp32", 0, solver="heun3", n=2, lengths=(9, 14), T=20, label="tiny")
+
+
+def c_bf16_simt():
+    check_estimator("bf16", 1 | 2 | 8, label="tiny simt-gemm simt-attn")
+    check_solve("bf16", 1 | 2 | 8, label="tiny simt-gemm simt-attn")
+
+
+def c_debug_gemm():
+    import torch
+    import matcha_tts_24k_b200 as P
+    ora, m = _models(TINY, "euler", "bf16", 1)
+    m.refresh(torch.device("cuda", 0))
+    lib, h = m._lib, m._handle
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K, taps) in [(128, 64, 64, 1), (256, 128, 128, 1), (300, 192, 256, 1), (1000, 384, 384, 3), (517, 160, 320, 3),
+                            (4096, 1536, 384, 1), (333, 100, 384, 1), (2048, 384, 1536, 1)]:
+        a = (torch.randn(M, K, generator=g)).bfloat16().cuda()
+        w = (torch.randn(taps * N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+        shifts = [0] if taps == 1 else [-1, 0, 1]
+        sh = (C.c_int32 * taps)(*shifts)
+        d_tc = torch.full((M, N), float("nan"), device="cuda")
+        d_si = torch.full((M, N), float("nan"), device="cuda")
+        P.native.check(lib, h, lib.cfm_debug_gemm(h, a.data_ptr(), w.data_ptr(), d_si.data_ptr(), M, N, K, taps, sh, 0, None))
+        P.native.check(lib, h, lib.cfm_debug_gemm(h, a.data_ptr(), w.data_ptr(), d_tc.data_ptr(), M, N, K, taps, sh, 1, None))
+        torch.cuda.synchronize()
+        ref = torch.zeros(M, N, dtype=torch.float64)
+        ad, wd = a.double().cpu(), w.double().cpu()
+        for t, s in enumerate(shifts):
+            sa = torch.zeros_like(ad)
+            if s == 0: sa = ad
+            elif s < 0: sa[-s:] = ad[:s]
+            else: sa[:-s] = ad[s:]
+            ref += sa @ wd[t * N:(t + 1) * N].T
+        print(f"[gemm M={M} N={N} K={K} taps={taps}] simt_vs_ref={rel(d_si, ref):.3e} tc_vs_ref={rel(d_tc, ref):.3e} "
+              f"tc_nan={int(torch.isnan(d_tc).sum())}")
+
+
+def c_bf16_tc_gemm():
+    check_estimator("bf16", 1 | 8 | 4, label="tiny tc-gemm unfused-stats simt-attn")
+    check_estimator("bf16", 1 | 8, label="tiny tc-gemm fused-stats simt-attn")
+    check_estimator("bf16", 1 | 8, lengths=(9, 30, 1, 2), T=64, label="tiny-padded tc-gemm simt-attn")
+    check_solve("bf16", 8, label="tiny tc-gemm graph simt-attn")
+
+
+def c_bf16_tc_attn():
+    check_estimator("bf16", 1 | 2, dec=TINY64, label="tiny64 simt-gemm TC-attn")
+    check_estimator("bf16", 1 | 2 | 8, dec=TINY64, label="tiny64 simt-gemm simt-attn (baseline)")
+    check_estimator("bf16", 1 | 2, dec=TINY64, lengths=(300, 129, 5), T=300, label="tiny64-long simt-gemm TC-attn")
+    check_estimator("bf16", 1 | 2 | 8, dec=TINY64, lengths=(300, 129, 5), T=300, label="tiny64-long simt-gemm simt-attn")
+    check_estimator("bf16", 1 | 2, dec=TINY64, lengths=(300, 129, 5), T=400, label="tiny64-long-padded simt-gemm TC-attn")
+    check_estimator("bf16", 1 | 2 | 8, dec=TINY64, lengths=(300, 129, 5), T=400, label="tiny64-long-padded simt-gemm simt-attn")
+    check_solve("bf16", 0, dec=TINY64, lengths=(300, 129, 5), T=300, label="tiny64 all-tc graph")
+
+
+def c_prod():
+    import torch
+    import matcha_tts_24k_b200 as P
+    for flags, label in ((8, "tc-gemm simt-attn"), (0, "all-tc")):
+        check_solve("bf16", flags, dec=P.synthetic.PROD, lengths=(120, 77), T=120, n=2, label="prod " + label)
+    check_solve("fp32", 0, dec=P.synthetic.PROD, lengths=(60, 41), T=60, n=2, label="prod fp32")
+
+
+def c_time():
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    for flags, label in ((8, "tc-gemm simt-attn"), (0, "all-tc")):
+        cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+        m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16", flags=flags).eval().cuda()
+        P.synthetic.fill_named_seed(m.estimator, 1234)
+        lengths = [938] * 32
+        mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+        ts = torch.linspace(0, 1, 11, device="cuda")
+        for _ in range(2):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        fl = P.synthetic.algorithmic_flops(lengths, 384, 10)
+        print(f"[time cfg2 {label}] {ms:.2f} ms/solve  {sum(lengths)/ms*1e3:.3e} frames/s  {fl/ms/1e9:.1f} TFLOP/s "
+              f"finite={bool(torch.isfinite(out).all())} info={m.plan_info()}")
+
+
+def c_trace():
+    """Bisect the schedule: compare intermediate buffers (fp32 mode, SIMT kernels, 7 launches per resnet / block)
+    against hooks on the dense oracle.  Valid rows per utterance (+ the pad-token row for the residual stream)."""
+    import torch
+    import matcha_tts_24k_b200 as P
+    lengths, T = [40, 33, 17], 40
+    ora, m = _models(TINY, "euler", "fp32", 1)
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=7, T=T)
+    caps = {}
+    est = ora.estimator
+    def hook(name, tr=False):
+        def f(mod, inp, out):
+            caps[name] = (out.transpose(1, 2) if not tr else out).detach()
+        return f
+    est.down_blocks[0][0].register_forward_hook(hook("d0.res"))
+    est.down_blocks[0][1][0].register_forward_hook(hook("d0.tb0", True))
+    est.down_blocks[0][1][1].register_forward_hook(hook("d0.tb1", True))
+    est.down_blocks[0][2].register_forward_hook(hook("d0.tail"))
+    est.down_blocks[1][0].register_forward_hook(hook("d1.res"))
+    est.down_blocks[1][1][1].register_forward_hook(hook("d1.tb1", True))
+    est.down_blocks[1][2].register_forward_hook(hook("d1.tail"))
+    est.mid_blocks[1][1][1].register_forward_hook(hook("m1.tb1", True))
+    est.up_blocks[0][1][1].register_forward_hook(hook("u0.tb1", True))
+    est.up_blocks[0][2].register_forward_hook(hook("u0.tail"))
+    est.up_blocks[1][1][1].register_forward_hook(hook("u1.tb1", True))
+    est.up_blocks[1][2].register_forward_hook(hook("u1.tail"))
+    est.final_block.register_forward_hook(hook("final_block"))
+    with torch.inference_mode():
+        v_ref = est(z, mask, mu, torch.tensor(0.3))
+    lib, hd = None, None
+    pts = [(8, "X1", "d0.res", 0, True), (15, "X1", "d0.tb0", 0, True), (22, "X1", "d0.tb1", 0, True),
+           (23, "sin2", "d0.tail", 1, False), (30, "X2", "d1.res", 1, True), (44, "X2", "d1.tb1", 1, True),
+           (45, "sin2", "d1.tail", 1, False), (87, "X2", "m1.tb1", 1, True), (108, "X2", "u0.tb1", 1, True),
+           (110, "cat1", "u0.tail", 0, False), (131, "X1", "u1.tb1", 0, True), (132, "hact1", "u1.tail", 0, False),
+           (135, "sin1", "final_block", 0, False)]
+    zc, mc, muc = z.cuda(), mask.cuda(), mu.cuda()
+    m.estimator(zc, mc, muc, torch.tensor(0.3))
+    lib, hd = m._lib, m._handle
+    for stop, buf, name, res, with_pad in pts:
+        lib.cfm_debug_stop_after(hd, stop)
+        m.estimator(zc, mc, muc, torch.tensor(0.3))
+        got = m.debug_read(buf)
+        ref = caps[name]  # (B, T_res, C)
+        C_ = ref.shape[2]
+        msgs = []
+        start = 0
+        for b, L in enumerate(lengths):
+            L2 = (L + 1) // 2
+            Lr = L if res == 0 else L2
+            s = 2 * start if res == 0 else start
+            g = got[s:s + Lr, :C_]
+            r = ref[b, :Lr]
+            e = rel(g, r)
+            ep = float("nan")
+            Tr = ref.shape[1]
+            if with_pad and Lr < Tr:
+                ep = rel(got[s + Lr, :C_], ref[b, Lr])
+            msgs.append(f"utt{b}(L={Lr}) valid={e:.2e} pad={ep:.2e}")
+            start += L2 + 2
+        print(f"[trace stop={stop} {buf} vs {name}] " + "  ".join(msgs))
+    lib.cfm_debug_stop_after(hd, -1)
+    v = m.estimator(zc, mc, muc, torch.tensor(0.3))
+    for b, L in enumerate(lengths):
+        print(f"[trace final v utt{b}] rel={rel(v[b, :, :L], v_ref[b, :, :L]):.3e}")
+    print("sinemb", rel(m.debug_read("sinemb")[0], __import__("oracle.cfm_oracle", fromlist=["x"]).sinusoidal_embedding(torch.tensor(0.3), 200)[0]))
+
+
+def c_perm():
+    """Which component makes results depend on utterance order?"""
+    import torch
+    import matcha_tts_24k_b200 as P
+    lengths = [400, 123, 398, 57, 256, 311]
+    perm = [4, 0, 5, 2, 1, 3]
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=9, T=400)
+    for prec, flags, label in (("fp32", 0, "fp32 simt"), ("bf16", 2 | 8, "bf16 simt-gemm simt-attn"), ("bf16", 2, "bf16 simt-gemm TC-attn"),
+                               ("bf16", 8 | 4, "bf16 TC-gemm unfused simt-attn"), ("bf16", 8, "bf16 TC-gemm fused simt-attn"),
+                               ("bf16", 0, "bf16 all-tc")):
+        for dec, dl in ((TINY64, "tiny64"), (P.synthetic.PROD, "prod")):
+            if prec == "fp32" and dl == "prod":
+                continue
+            ora, m = _models(dec, "euler", prec, flags | 1)
+            t = torch.tensor(0.4)
+            full = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t).cpu()
+            again = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t).cpu()
+            sh = m.estimator(z[perm].cuda(), mask[perm].cuda(), mu[perm].cuda(), t).cpu()
+            errs = [rel(sh[j], full[i]) for j, i in enumerate(perm)]
+            print(f"[perm {label} {dl}] repeat={rel(again, full):.2e} perm_max={max(errs):.2e} per-utt=" + " ".join(f"{e:.1e}" for e in errs))
+
+
+def c_stats():
+    """Compare the fused-epilogue GroupNorm sums against the stand-alone statistics kernel, site 0 (first conv)."""
+    import torch
+    import matcha_tts_24k_b200 as P
+    lengths = [400, 123, 398, 57, 256, 311]
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=9, T=400)
+    res = {}
+    for flags, stop, label in ((1 | 8 | 4, 3, "unfused"), (1 | 8, 2, "fused")):
+        ora, m = _models(TINY64, "euler", "bf16", flags)
+        t = torch.tensor(0.4)
+        m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t)
+        m._lib.cfm_debug_stop_after(m._handle, stop)
+        m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t)
+        res[label] = m.debug_read("stats")[:len(lengths)].clone()
+        res[label + "_h"] = m.debug_read("hraw1").clone()
+    torch.set_printoptions(linewidth=200, precision=6)
+    print("hraw equal:", rel(res["fused_h"], res["unfused_h"]))
+    d = (res["fused"] - res["unfused"]).abs() / res["unfused"].abs().clamp_min(1e-6)
+    for b in range(len(lengths)):
+        print(f"utt{b} L={lengths[b]} max rel diff={float(d[b].max()):.3e}\n  fused  ={res['fused'][b][:6].tolist()}\n  unfused={res['unfused'][b][:6].tolist()}")
+
+
+def c_stats_all():
+    import torch
+    import matcha_tts_24k_b200 as P
+    lengths = [400, 123, 398, 57, 256, 311]
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=9, T=400)
+    res = {}
+    for flags, label in ((1 | 8 | 4, "unfused"), (1 | 8, "fused")):
+        ora, m = _models(TINY64, "euler", "bf16", flags)
+        m.estimator(z.cuda(), mask.cuda(), mu.cuda(), torch.tensor(0.4))
+        res[label] = m.debug_read("stats").clone().view(-1, len(lengths), 16)
+    d = (res["fused"] - res["unfused"]).abs() / res["unfused"].abs().clamp_min(1e-3)
+    for site in range(d.shape[0]):
+        print(f"site {site}: " + " ".join(f"utt{b}={float(d[site, b].max()):.1e}" for b in range(len(lengths))))
+        bad = (d[site] > 1e-3).nonzero()
+        for b, k in bad[:4].tolist():
+            print(f"    utt{b} k={k} fused={float(res['fused'][site, b, k]):.6f} unfused={float(res['unfused'][site, b, k]):.6f}")
+
+
+CHECKS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("c_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        CHECKS[sys.argv[2]]()
+        sys.exit(0)
+    names = sys.argv[1:] or list(CHECKS)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a") as log:
+        for n in names:
+            t0 = time.time()
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True, text=True, timeout=420)
+                tail = "\n".join((p.stdout + "\n" + p.stderr[-3000:]).strip().splitlines()[-40:])
+                msg = f"=== {n}: exit {p.returncode} in {time.time()-t0:.0f}s\n{tail}\n"
+            except subprocess.TimeoutExpired as e:
+                msg = f"=== {n}: TIMEOUT\n{(e.stdout or b'')[-2000:]}\n"
+            print(msg, flush=True)
+            log.write(msg)
+            log.flush()
