@@ -1,7 +1,7 @@
 // Tensor-core flash attention for sm_100a (bf16, head_dim 64): softmax(Q K^T d^-1/2 + key_bias) V per (utterance, head).
 //
-// One CTA per (utterance, head, 128-query tile); 192 threads = TMA warp, MMA warp, 4 softmax warps (one query row per
-// thread).  Per 128-key tile:
+// One CTA per (utterance, head, 128-query tile); 320 threads = TMA warp, MMA warp, 8 softmax warps (two threads per
+// query row, each owning half of the key columns and half of the output columns).  Per 128-key tile:
 //     S  = Q K^T      tcgen05.mma  M128 N128 K64   (Q, K tiles K-major, 128B-swizzled by TMA)    -> TMEM cols [0,128)
 //     P  = exp2(...)  tcgen05.ld S -> registers -> online softmax -> bf16 P written to smem in the UMMA K-major layout
 //     PV = P V        tcgen05.mma  M128 N64 K128   (V tile MN-major straight from TMA)            -> TMEM cols [128,192)
@@ -21,11 +21,22 @@ struct AttnTcCfg {
   static constexpr int D = 64, QT = 128, KT = 128;
   static constexpr int Q_BYTES = QT * D * 2, K_BYTES = KT * D * 2, V_BYTES = KT * D * 2, P_BYTES = QT * KT * 2;
   static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 192;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;         // 6 mbarriers + TMEM slot (64 B)
+  static constexpr int OFF_RED = OFF_BAR + 64;            // [2][128] floats: row max / row sum exchange between column halves
+  static constexpr int SMEM_BYTES = OFF_RED + 2 * QT * 4 + 1024;
+  static constexpr int N_SOFTMAX_WARPS = 8;
+  static constexpr int THREADS = 64 + 32 * N_SOFTMAX_WARPS;
   static constexpr int TMEM_COLS = 256;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttTable* __restrict__ utt,
@@ -36,6 +47,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t *bar_q = bars + 0, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_p = bars + 4, *bar_pv = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* red = reinterpret_cast<float*>(smem + Cfg::OFF_RED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int4 w = work[blockIdx.x];
@@ -51,7 +63,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
     ptx::mbar_init(bar_k, 1);
     ptx::mbar_init(bar_v, 1);
     ptx::mbar_init(bar_s, 1);
-    ptx::mbar_init(bar_p, 128);
+    ptx::mbar_init(bar_p, 32 * Cfg::N_SOFTMAX_WARPS);
     ptx::mbar_init(bar_pv, 1);
     ptx::fence_mbar_init();
   }
@@ -70,7 +82,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
       ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
       ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_qkv, bar_q, head * Cfg::D, row0 + q0);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j > 0) ptx::mbar_wait(bar_s, (j - 1) & 1);  // S_{j-1} issued & complete: K buffer free
+        if (j > 0) ptx::mbar_wait(bar_s, (j - 1) & 1);  // S_{j-1} complete: K buffer free
         ptx::mbar_expect_tx(bar_k, Cfg::K_BYTES);
         ptx::tma_load_2d(smem + Cfg::OFF_K, &tm_qkv, bar_k, inner + head * Cfg::D, row0 + j * Cfg::KT);
         if (j > 0) ptx::mbar_wait(bar_pv, (j - 1) & 1);  // PV_{j-1} complete: V buffer free
@@ -104,106 +116,113 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
       }
     }
   } else {
-    // ---------------- softmax / correction / epilogue: one query row per thread
-    const int quarter = warp & 3;
+    // ---------------- softmax / correction / epilogue: two threads per query row.
+    // Thread (row r, half hc) owns key columns [64 hc, 64 hc + 64) of S and output columns [32 hc, 32 hc + 32) of O.
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may touch
+    const int hc = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float pad_bias = u.pad_key_bias * 1.4426950408889634f;
-    float o[Cfg::D];
+    float o[32];
 #pragma unroll
-    for (int d = 0; d < Cfg::D; ++d) o[d] = 0.f;
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
     float mrun = -INFINITY, lrun = 0.f;
-    uint8_t* p_row = smem + Cfg::OFF_P + r * 128;
+    uint8_t* p_row = smem + Cfg::OFF_P + hc * (Cfg::QT * 128) + r * 128;  // K-block hc of the P tile, row r
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
-      const int k0 = j * Cfg::KT;
-      const bool ragged = (k0 + Cfg::KT > L);  // tile holds the pad token and/or rows past this utterance
+      const int k0 = j * Cfg::KT + hc * 64;
+      const bool ragged = (k0 + 64 > L);  // this half holds the pad token and/or rows past this utterance
       ptx::mbar_wait(bar_s, ph);
       ptx::tc_fence_after();
-      // pass 1: row maximum
+      // pass 1: maximum over this thread's 64 columns, then exchange with the partner half
       float mt = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < Cfg::KT; c += 32) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_s + lane_off + c, a);
-        ptx::tmem_ld16(tmem_s + lane_off + c + 16, b);
+        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c, a);
+        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c + 16, b);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]) * scale_log2;
+          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]);
           if (ragged) {
             const int key = k0 + c + i;
-            t = key < L ? t : (key == L ? t + pad_bias : -INFINITY);
+            t = key < L ? t : (key == L ? t + pad_bias / scale_log2 : -INFINITY);
           }
           mt = fmaxf(mt, t);
         }
       }
-      const float mnew = fmaxf(mrun, mt);
-      const float corr = exp2f(mrun - mnew);
+      red[hc * Cfg::QT + r] = mt;
+      named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
+      mt = fmaxf(mt, red[(hc ^ 1) * Cfg::QT + r]);
+      const float mnew = fmaxf(mrun, mt * scale_log2);  // finite: key 0 of the first tile is always valid
+      const float corr = ex2_approx(mrun - mnew);
       float psum = 0.f;
-      // pass 2: P = exp2(t - m) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7))
-#pragma unroll 1
-      for (int c = 0; c < Cfg::KT; c += 32) {
+      // pass 2: P = exp2(s * c - m) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_s + lane_off + c, a);
-        ptx::tmem_ld16(tmem_s + lane_off + c + 16, b);
+        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c, a);
+        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c + 16, b);
         ptx::tmem_ld_wait();
-        float p[32];
+        float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]) * scale_log2;
+          float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
           if (ragged) {
             const int key = k0 + c + i;
             t = key < L ? t : (key == L ? t + pad_bias : -INFINITY);
           }
-          p[i] = exp2f(t - mnew);
-          psum += p[i];
+          pv[i] = ex2_approx(t);
+          psum += pv[i];
         }
-        uint8_t* blk = p_row + (c >> 6) * (Cfg::QT * 128);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c & 63) >> 3) + g;
+          const int chunk = (c >> 3) + g;
           uint4 pk;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(p[8 * g + 0], p[8 * g + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(p[8 * g + 2], p[8 * g + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p[8 * g + 4], p[8 * g + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(p[8 * g + 6], p[8 * g + 7]);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[8 * g + 0], pv[8 * g + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[8 * g + 2], pv[8 * g + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[8 * g + 4], pv[8 * g + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[8 * g + 6], pv[8 * g + 7]);
           pk.x = *reinterpret_cast<uint32_t*>(&h0);
           pk.y = *reinterpret_cast<uint32_t*>(&h1);
           pk.z = *reinterpret_cast<uint32_t*>(&h2);
           pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = pk;
         }
       }
       lrun = lrun * corr + psum;
       mrun = mnew;
 #pragma unroll
-      for (int d = 0; d < Cfg::D; ++d) o[d] *= corr;
+      for (int d = 0; d < 32; ++d) o[d] *= corr;
       ptx::tc_fence_before();
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::mbar_arrive(bar_p);
       ptx::mbar_wait(bar_pv, ph);
       ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < Cfg::D; c += 32) {
+      {
         uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_pv + lane_off + c, a);
-        ptx::tmem_ld16(tmem_pv + lane_off + c + 16, b);
+        ptx::tmem_ld16(tmem_pv + lane_off + hc * 32, a);
+        ptx::tmem_ld16(tmem_pv + lane_off + hc * 32 + 16, b);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          o[c + i] += __uint_as_float(a[i]);
-          o[c + 16 + i] += __uint_as_float(b[i]);
+          o[i] += __uint_as_float(a[i]);
+          o[16 + i] += __uint_as_float(b[i]);
         }
       }
     }
     ptx::tc_fence_before();
+    // total row sum = both halves
+    red[hc * Cfg::QT + r] = lrun;
+    named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
+    lrun += red[(hc ^ 1) * Cfg::QT + r];
     const int qi = q0 + r;
     if (qi < nk) {
       const float inv = 1.f / lrun;
-      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
+      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D + hc * 32;
 #pragma unroll
-      for (int d = 0; d < Cfg::D; d += 8) {
+      for (int d = 0; d < 32; d += 8) {
         uint4 pk;
         __nv_bfloat162 h0 = __floats2bfloat162_rn(o[d + 0] * inv, o[d + 1] * inv);
         __nv_bfloat162 h1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv);

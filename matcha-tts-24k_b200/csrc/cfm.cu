@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -111,6 +112,8 @@ struct cfm_handle {
   Plan* plan = nullptr;
   EncodeTiledFn encode = nullptr;
   int sm_count = 148;
+  int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
+  int cluster = 2;                              // CTAs sharing one weight tile via TMA multicast
   long long launch_counter = 0;
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
@@ -336,16 +339,38 @@ template <int BN>
 int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
                  cudaStream_t s) {
   using Cfg = TcCfg<BN>;
-  const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
-  const int grid = std::min(tiles, h->sm_count);
-  gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(a0, a1, w, p);
-  CK(cudaGetLastError());
+  const int CL = p.cluster;
+  const int m_super = ((p.M + 127) / 128 + CL - 1) / CL;
+  const int super_tiles = m_super * ((p.N + BN - 1) / BN);
+  const int clusters = std::min(super_tiles, h->max_clusters[CL]);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(clusters * CL), cfg.blockDim = dim3(Cfg::THREADS), cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, a0, a1, w, p));
   return 0;
 }
 
 template <int BN>
 int set_tc_attr(cfm_handle* h) {
   CK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+  if (BN == 192) {  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
+    for (int CL = 1; CL <= 4; CL *= 2) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(h->sm_count / CL * CL), cfg.blockDim = dim3(TcCfg<BN>::THREADS), cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr, cfg.numAttrs = 1;
+      int n = 0;
+      CK(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN>, &cfg));
+      h->max_clusters[CL] = std::max(1, n);
+    }
+  }
   return 0;
 }
 
@@ -370,7 +395,8 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     const int src = p.A[i] ? i : 0;
     CKR(make_tmap(h, &tmA[i], p.A[src], p.lda[src], p.a_rows[src], p.lda[src] * 2, 64, 128));
   }
-  CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, bn));
+  p.cluster = h->cluster;
+  CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, bn / p.cluster));
   switch (bn) {
     case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, p, s);
     case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
@@ -779,6 +805,10 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h->bf = cfg->precision == CFM_PREC_BF16;
   h->es = h->bf ? 2 : 4;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("CFM_B200_CLUSTER")) {
+    const int c = atoi(e);
+    if (c == 1 || c == 2 || c == 4) h->cluster = c;
+  }
   auto bail = [&](int code) {
     g_create_error = h->err;
     delete h;
@@ -1118,6 +1148,48 @@ int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches) {
   if (!h) return CFM_ERR_INVALID;
   h->stop_after = n_launches;
   return 0;
+}
+
+// Debug: tensor-core GEMM in a chosen epilogue mode with the CTA-0 role profile.  mode: 0 = bf16 store, 1 = fp32 store,
+// 2 = fp32 residual add in place (d_f32 is both residual and output).  prof (device, >= 16 u64) receives cycle counters:
+// [0] producer total [1] producer waiting for free stages [2] MMA total [3] MMA waiting for operands [4] MMA waiting for a
+// free accumulator [5] epilogue warp total [6] epilogue waiting for an accumulator [8] tiles done by CTA 0.
+int cfm_debug_gemm_profile(cfm_handle* h, const void* a, const void* w, float* d_f32, void* d_bf16, int32_t M, int32_t N,
+                           int32_t K, int32_t n_taps, const int32_t* shifts, int32_t mode, unsigned long long* prof,
+                           void* stream) {
+  if (!h || !a || !w) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->bf) return fail(h, CFM_ERR_INVALID, "needs a bf16 handle");
+  CK(cudaSetDevice(h->cfg.device));
+  GemmW gw;
+  gw.w = const_cast<void*>(w), gw.N = N, gw.K = K, gw.Kp = K, gw.n_taps = n_taps, gw.n_stride = N;
+  GemmParams p = gemm_base(M, a, K, M, gw, shifts, nullptr);
+  p.prof = prof;
+  if (mode == 0) p.mode = EPI_STORE, p.out_act = d_bf16, p.ld_act = N;
+  else if (mode == 1) p.mode = EPI_STATS, p.fused_stats = 0, p.out_f32 = d_f32, p.ld_f32 = N;
+  else if (mode == 3) {  // fp32 store + fused GroupNorm statistics on synthetic 942-row utterances
+    static int* info = nullptr;
+    static double* stats = nullptr;
+    static float* bias = nullptr;
+    static int info_rows = 0;
+    if (info_rows < M) {
+      std::vector<int> hinfo(M);
+      for (int i = 0; i < M; ++i) hinfo[i] = (i / 942) | ROW_VALID | ROW_INSTAT;
+      CK(cudaMalloc(&info, (size_t)M * 4));
+      CK(cudaMemcpy(info, hinfo.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&stats, (size_t)(M / 942 + 1) * 16 * 8 * 64));
+      CK(cudaMemset(stats, 0, (size_t)(M / 942 + 1) * 16 * 8 * 64));
+      CK(cudaMalloc(&bias, 4096 * 4));
+      CK(cudaMemset(bias, 0, 4096 * 4));
+      info_rows = M;
+    }
+    p.mode = EPI_STATS, p.fused_stats = 1, p.out_f32 = d_f32, p.ld_f32 = N, p.row_info = info, p.stats = stats;
+    p.group_ch = N / 8, p.bias = bias;
+  } else p.mode = EPI_RESID, p.resid = d_f32, p.ld_resid = N, p.out_f32 = d_f32, p.ld_f32 = N;
+  const int saved = h->cfg.flags;
+  h->cfg.flags &= ~CFM_FLAG_SIMT_GEMM;
+  int r = launch_gemm(h, p, true, static_cast<cudaStream_t>(stream));
+  h->cfg.flags = saved;
+  return r;
 }
 
 int cfm_debug_gemm(cfm_handle* h, const void* a, const void* w, float* d, int32_t M, int32_t N, int32_t K, int32_t n_taps,

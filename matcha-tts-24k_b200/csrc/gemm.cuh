@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace cfm {
@@ -71,6 +73,8 @@ struct GemmParams {
   const float* kin[3];
   float* kout;
   long long ld_k;
+  int cluster;  // CTAs per cluster sharing one weight tile via TMA multicast (1, 2 or 4)
+  unsigned long long* prof;  // debug: CTA 0 writes per-role cycle counters (see gemm_tc_kernel); nullptr = off
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -93,9 +97,10 @@ template <> struct ActIO<bf16> {
 };
 
 template <typename T, int NV>
-__device__ __forceinline__ void store_act(T* dst, const float (&v)[NV], bool vec_ok) {
+__device__ __forceinline__ void store_act(T* dst, const float (&v)[NV], bool /*unused*/ = true) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(dst);
   if constexpr (sizeof(T) == 2 && NV % 8 == 0) {
-    if (vec_ok) {
+    if ((addr & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) {
         uint4 u;
@@ -112,8 +117,22 @@ __device__ __forceinline__ void store_act(T* dst, const float (&v)[NV], bool vec
       return;
     }
   }
+  if constexpr (sizeof(T) == 2 && NV % 4 == 0) {
+    if ((addr & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        uint2 u;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(dst + i) = u;
+      }
+      return;
+    }
+  }
   if constexpr (sizeof(T) == 4 && NV % 4 == 0) {
-    if (vec_ok) {
+    if ((addr & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4)
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -352,6 +371,149 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Lean epilogue of the tensor-core kernel for one 32x32 accumulator block of one warp.
+// Phase 1 (caller): the thread that owns TMEM lane r wrote row r of the block into `stg` (row stride EPI_LD floats).
+// Phase 2 (here): lane (rs = lane/8, cg = lane%8) owns columns n..n+3 of rows rs, rs+4, ..., rs+28, so that 8 lanes
+// cover 32 consecutive columns of a row: global loads / stores are full 128-byte (fp32) or 64-byte (bf16) row segments.
+// Everything that depends only on the column (bias, SnakeBeta constants) is loaded once per block.
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  return u;
+}
+
+template <int MODE, int EPI_LD>
+__device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int m0, int n, int lane, int info,
+                                          bool stats_uniform, bool do_stats, uint32_t warp_slots, int g_first) {
+  const int rs = lane >> 3, cg = lane & 7;
+  const bool col_ok = n < p.N;  // N % 4 == 0: a lane's 4 columns are all inside or all outside
+  if (!col_ok) n = 0;           // keep the lane in the shuffles below with harmless addresses, stores predicated off
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  float4 ea4, ib4;
+  if constexpr (MODE == EPI_SNAKE) {
+    ea4 = __ldg(reinterpret_cast<const float4*>(p.ea + n));
+    ib4 = __ldg(reinterpret_cast<const float4*>(p.ib + n));
+  }
+  float gs = 0.f, gss = 0.f;
+  int cur_utt = -1;
+  bf16* oact = reinterpret_cast<bf16*>(p.out_act);
+  // All global loads of the block are issued before any store: the residual stream is updated in place, so the compiler
+  // must otherwise order every load behind the previous row's store and exposes one memory round trip per row.
+  float4 rv[8];
+  if constexpr (MODE == EPI_RESID || MODE == EPI_ODE) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = m0 + it * 4 + rs;
+      rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M && col_ok && p.resid) rv[it] = *reinterpret_cast<const float4*>(p.resid + (long long)m * p.ld_resid + n);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rs;
+    const int m = m0 + r;
+    const float4 a = ptx::lds128(stg + (r * EPI_LD + cg * 4) * 4);
+    const int info_r = __shfl_sync(0xffffffffu, info, r);
+    if (m >= p.M || !col_ok) continue;
+    float x0 = a.x + b4.x, x1 = a.y + b4.y, x2 = a.z + b4.z, x3 = a.w + b4.w;
+    const bool valid = (info_r & ROW_VALID) != 0;
+    if constexpr (MODE == EPI_STORE) {
+      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+    } else if constexpr (MODE == EPI_STATS) {
+      *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
+      if (do_stats && (info_r & ROW_INSTAT)) {
+        // Rows are sorted by utterance, so a lane sees a non-decreasing utterance id; in a warp that straddles a segment
+        // boundary the running sums are flushed whenever the id changes (and once at the end), otherwise never here.
+        const int ur = info_r & ROW_UTT_MASK;
+        if (ur != cur_utt) {
+          if (cur_utt >= 0 && !stats_uniform) {
+            const long long o = ((long long)cur_utt * 8 + n / p.group_ch) * 2;
+            atomicAdd(p.stats + o, (double)gs);
+            atomicAdd(p.stats + o + 1, (double)gss);
+            gs = gss = 0.f;
+          }
+          cur_utt = ur;
+        }
+        gs += (x0 + x1) + (x2 + x3);
+        gss = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, gss))));
+      }
+    } else if constexpr (MODE == EPI_RESID) {
+      x0 += rv[it].x, x1 += rv[it].y, x2 += rv[it].z, x3 += rv[it].w;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
+      if (oact) {
+        if (!valid) x0 = x1 = x2 = x3 = 0.f;
+        *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+      }
+    } else if constexpr (MODE == EPI_SNAKE) {
+      float s0 = ActIO<bf16>::fsin(x0 * ea4.x), s1 = ActIO<bf16>::fsin(x1 * ea4.y);
+      float s2 = ActIO<bf16>::fsin(x2 * ea4.z), s3 = ActIO<bf16>::fsin(x3 * ea4.w);
+      x0 = fmaf(s0 * s0, ib4.x, x0), x1 = fmaf(s1 * s1, ib4.y, x1), x2 = fmaf(s2 * s2, ib4.z, x2), x3 = fmaf(s3 * s3, ib4.w, x3);
+      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+    } else if constexpr (MODE == EPI_MASK) {
+      if (!valid) x0 = x1 = x2 = x3 = 0.f;
+      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+    } else {  // EPI_ODE
+      if (!valid) x0 = x1 = x2 = x3 = 0.f;
+      float4 y = rv[it];
+      y.x = fmaf(p.c_v, x0, y.x), y.y = fmaf(p.c_v, x1, y.y), y.z = fmaf(p.c_v, x2, y.z), y.w = fmaf(p.c_v, x3, y.w);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (p.kin[j]) {
+          const float4 kv = *reinterpret_cast<const float4*>(p.kin[j] + (long long)m * p.ld_k + n);
+          y.x = fmaf(p.c_k[j], kv.x, y.x), y.y = fmaf(p.c_k[j], kv.y, y.y), y.z = fmaf(p.c_k[j], kv.z, y.z), y.w = fmaf(p.c_k[j], kv.w, y.w);
+        }
+      }
+      if (p.kout) *reinterpret_cast<float4*>(p.kout + (long long)m * p.ld_k + n) = make_float4(x0, x1, x2, x3);
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = y;
+      if (oact) {
+        if (!valid) y = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(y.x, y.y, y.z, y.w);
+      }
+    }
+  }
+  if constexpr (MODE == EPI_STATS) {
+    if (do_stats && !stats_uniform && cur_utt >= 0 && col_ok) {  // boundary warp: each lane flushes its last segment
+      const long long o = ((long long)cur_utt * 8 + n / p.group_ch) * 2;
+      atomicAdd(p.stats + o, (double)gs);
+      atomicAdd(p.stats + o + 1, (double)gss);
+    }
+    if (do_stats && stats_uniform) {  // reduce over the 4 row phases, then one atomic pair per 4-column group
+      gs += __shfl_xor_sync(0xffffffffu, gs, 8);
+      gss += __shfl_xor_sync(0xffffffffu, gss, 8);
+      gs += __shfl_xor_sync(0xffffffffu, gs, 16);
+      gss += __shfl_xor_sync(0xffffffffu, gss, 16);
+      const int utt = __shfl_sync(0xffffffffu, info, 0) & ROW_UTT_MASK;
+      if (warp_slots) {
+        // The whole tile is one utterance: combine the 8 column groups of this block that fall into the same GroupNorm
+        // group (segmented scan over cg), then the segment tails add into this warp's private smem slots.  No atomics,
+        // fixed order -> bitwise reproducible; the last warp of the tile reduces the 8 warps' slots (gemm_tc_kernel).
+        const int gid = col_ok ? n / p.group_ch - g_first : 64 + cg;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const float us = __shfl_up_sync(0xffffffffu, gs, o, 8), uss = __shfl_up_sync(0xffffffffu, gss, o, 8);
+          const int ug = __shfl_up_sync(0xffffffffu, gid, o, 8);
+          if (cg >= o && ug == gid) gs += us, gss += uss;
+        }
+        const int ng = __shfl_down_sync(0xffffffffu, gid, 1, 8);
+        if (rs == 0 && col_ok && (cg == 7 || ng != gid)) {
+          const uint32_t a = warp_slots + gid * 8;
+          ptx::sts32(a, ptx::lds32(a) + gs);
+          ptx::sts32(a + 4, ptx::lds32(a + 4) + gss);
+        }
+      } else if (rs == 0 && col_ok && (gs != 0.f || gss != 0.f)) {
+        const long long o = ((long long)utt * 8 + n / p.group_ch) * 2;
+        atomicAdd(p.stats + o, (double)gs);
+        atomicAdd(p.stats + o + 1, (double)gss);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 implementation.
 template <int BN>
@@ -361,16 +523,29 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_SMEM = 227 * 1024;
-  static constexpr int CTRL_BYTES = 256;
-  static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + CTRL_BYTES;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int CTRL_BYTES = 2048;  // mbarriers + TMEM slot (256 B), GroupNorm partial sums [2 sets][8 warps][8 groups][2] + counters
   static constexpr int N_EPI_WARPS = 8;
+  static constexpr int EPI_LD = 36;  // padded row (floats): 16-byte aligned rows, conflict-free 128-bit accesses
+  static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;     // per-warp staging for the coalesced epilogue
+  static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + CTRL_BYTES + EPI_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int THREADS = 128 + 32 * N_EPI_WARPS;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
+
+// mbarrier wait that optionally accumulates the cycles spent waiting (debug profile of CTA 0).
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, bool prof, unsigned long long& acc) {
+  if (!prof) {
+    ptx::mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  ptx::mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
@@ -387,9 +562,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Cluster of CL CTAs = CL consecutive m-tiles of one n-tile ("super-tile"); every CTA of a cluster walks the same
+  // super-tile list in lock step (a CTA whose m-tile lies past M still runs: its loads are zero-filled, stores predicated).
+  const int CL = p.cluster;
+  const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1);
   const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
+  const int m_super = (m_tiles + CL - 1) / CL;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int n_tiles_total = m_tiles * n_tiles;
+  const int n_tiles_total = m_super * n_tiles;  // super-tiles
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   const int kb_per_tap = p.K / Cfg::BK;
   const int k_iters = p.n_taps * kb_per_tap;
 
@@ -401,7 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
@@ -409,12 +591,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     ptx::fence_mbar_init();
   }
+  // GroupNorm partial sums: [2 accumulator sets][8 epilogue warps][8 groups][2] floats, then 2 arrival counters
+  const uint32_t gn_slots = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  const uint32_t gn_counters = gn_slots + 2 * 8 * 8 * 2 * 4;
+  if (warp == 3) {
+    for (int i = lane; i < 2 * 8 * 8 * 2 + 2; i += 32) ptx::sts32(gn_slots + i * 4, 0.f);
+  }
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -423,21 +612,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * Cfg::BM, n0 = (tile % n_tiles) * BN;
+      const bool prof = p.prof != nullptr && blockIdx.x == 0;
+      unsigned long long w_empty = 0;
+      const long long t_start = clock64();
+      const int b_rows = BN / CL;  // this CTA's slice of the weight tile
+      for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters) {
+        const int m0 = ((tile / n_tiles) * CL + crank) * Cfg::BM, n0 = (tile % n_tiles) * BN;
         for (int t = 0; t < p.n_taps; ++t) {
           const GemmTap tap = p.taps[t];
           const CUtensorMap* tmA = tap.a_src ? &tmA1 : &tmA0;
           for (int kb = 0; kb < kb_per_tap; ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_prof(&empty_bar[stage], phase ^ 1, prof, w_empty);  // every CTA of the cluster released this stage
             ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             ptx::tma_load_2d(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
-            ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
+            if (CL == 1)
+              ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
+            else
+              ptx::tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * b_rows * 128, &tmW, &full_bar[stage], kb * Cfg::BK,
+                                     tap.w_row + n0 + crank * b_rows, cmask);
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
       }
+      if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one lane) =====================
@@ -446,14 +644,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+      const bool prof = p.prof != nullptr && blockIdx.x == 0;
+      unsigned long long w_full = 0, w_tempty = 0;
+      const long long t_start = clock64();
+      for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_prof(&tempty_bar[acc], acc_phase ^ 1, prof, w_tempty);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int it = 0; it < k_iters; ++it) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          mbar_wait_prof(&full_bar[stage], phase, prof, w_full);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -462,93 +663,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::umma_bf16(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
                            (it > 0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          if (CL == 1) ptx::umma_commit(&empty_bar[stage]);
+          else ptx::umma_commit_mcast(&empty_bar[stage], cmask);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
         ptx::umma_commit(&tfull_bar[acc]);
       }
+      if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps: TMEM -> registers -> global =====================
-    const int q = warp & 3;              // TMEM lane quarter this warp may touch
-    const int half = (warp - 4) >> 2;    // which half of the tile's columns
-    constexpr int COLS = BN / 2;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
-      const int m0 = (tile / n_tiles) * Cfg::BM, n0 = (tile % n_tiles) * BN + half * COLS;
-      const int m = m0 + q * 32 + lane;
-      const int info = load_row_info(p, m);
-      const bool do_stats = (p.mode == EPI_STATS) && p.fused_stats;
-      const int utt = info & ROW_UTT_MASK;
-      const bool instat = (info & ROW_INSTAT) != 0;
-      bool uniform = false;
-      if (do_stats) uniform = __all_sync(0xffffffffu, utt == __shfl_sync(0xffffffffu, utt, 0));
-      float gs = 0.f, gss = 0.f;
-      int cur_g = -1;
-      auto flush = [&]() {
-        if (cur_g < 0) return;
-        if (uniform) {
-          float a = gs, b = gss;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          if (lane == 0 && (a != 0.f || b != 0.f)) {
-            atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2, (double)a);
-            atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2 + 1, (double)b);
-          }
-        } else if (instat) {
-          atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2, (double)gs);
-          atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2 + 1, (double)gss);
-        }
-        gs = gss = 0.f;
-      };
-
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + half * COLS + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < COLS; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld16(taddr + c, r);
-        ptx::tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (do_stats) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int nn = n0 + c + 8 * h;
-            if (nn < p.N) {
-              const int g = nn / p.group_ch;
-              if (g != cur_g) {
-                flush();
-                cur_g = g;
-              }
-              if (instat) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float xv = v[8 * h + i] + __ldg(p.bias + nn + i);
-                  gs += xv;
-                  gss = fmaf(xv, xv, gss);
-                }
-              }
+    // ===================== epilogue warps: TMEM -> registers -> smem transpose -> coalesced global I/O ============
+    // tcgen05.ld hands each thread one accumulator ROW; touching global memory in that shape makes every warp
+    // instruction hit 32 different cache lines, so each 32x32 block goes through a per-warp smem tile (epi_block).
+    // The mode switch is hoisted out of all loops: each mode runs its own specialised copy of the loop.
+    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * 32 * Cfg::EPI_LD * 4;
+    auto run = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      const int q = warp & 3;            // TMEM lane quarter this warp may touch
+      const int half = (warp - 4) >> 2;  // the two warps of a quarter alternate over the 32-column blocks
+      const int cg = lane & 7;
+      int local = 0;
+      const bool prof = p.prof != nullptr && blockIdx.x == 0 && warp == 4;
+      unsigned long long w_tfull = 0;
+      const long long t_start = clock64();
+      for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        const int m0 = ((tile / n_tiles) * CL + crank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
+        const int info = load_row_info(p, m0 + lane);
+        bool do_stats = false, uniform = false;
+        uint32_t warp_slots = 0;
+        int tile_utt = 0, g_first = 0;
+        if constexpr (MODE == EPI_STATS) {
+          do_stats = p.fused_stats != 0;
+          const int utt = info & ROW_UTT_MASK;
+          if (do_stats) {
+            uniform = __all_sync(0xffffffffu, utt == __shfl_sync(0xffffffffu, utt, 0));
+            // If the 128 rows of the tile are one utterance (the common case) the sums are gathered per CTA in smem.
+            const int mt = m0 - q * 32;
+            const int u_lo = __ldg(p.row_info + min(mt, p.M - 1)) & ROW_UTT_MASK;
+            const int u_hi = __ldg(p.row_info + min(mt + Cfg::BM - 1, p.M - 1)) & ROW_UTT_MASK;
+            if (u_lo == u_hi && mt < p.M && (BN % p.group_ch) == 0 && p.row_mul == 1) {
+              warp_slots = gn_slots + ((acc * 8 + (warp - 4)) * 16) * 4;
+              tile_utt = u_lo, g_first = n0 / p.group_ch;
+              uniform = true;  // rows past M carry no ROW_INSTAT flag and add nothing
             }
           }
         }
-        if (m < p.M) epi_apply<bf16, 16>(p, m, n0 + c, v, info);
+        mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int blk = half; blk < BN / 32; blk += 2) {
+          const int c = blk * 32;
+          uint32_t r0[16], r1[16];
+          ptx::tmem_ld16(taddr + c, r0);
+          ptx::tmem_ld16(taddr + c + 16, r1);
+          ptx::tmem_ld_wait();
+          const uint32_t srow = stg + lane * Cfg::EPI_LD * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ptx::sts128(srow + i * 16, __uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]), __uint_as_float(r0[4 * i + 2]),
+                        __uint_as_float(r0[4 * i + 3]));
+            ptx::sts128(srow + 64 + i * 16, __uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]),
+                        __uint_as_float(r1[4 * i + 2]), __uint_as_float(r1[4 * i + 3]));
+          }
+          __syncwarp();
+          epi_block<MODE, Cfg::EPI_LD>(p, stg, m0, n0 + c + cg * 4, lane, info, uniform, do_stats, warp_slots, g_first);
+          __syncwarp();
+        }
+        if constexpr (MODE == EPI_STATS) {
+          if (warp_slots) {  // the last of the 8 epilogue warps to finish this tile reduces and flushes (16 atomics / tile)
+            __syncwarp();
+            uint32_t old = 0;
+            if (lane == 0) {
+              __threadfence_block();
+              old = ptx::atoms_add_u32(gn_counters + acc * 4, 1);
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == Cfg::N_EPI_WARPS - 1) {
+              __threadfence_block();
+              if (lane < 16) {
+                double v = 0.0;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) {
+                  const uint32_t a = gn_slots + ((acc * 8 + w8) * 16 + lane) * 4;
+                  v += (double)ptx::lds32(a);
+                  ptx::sts32(a, 0.f);
+                }
+                if (v != 0.0) atomicAdd(p.stats + ((long long)tile_utt * 8 + g_first + (lane >> 1)) * 2 + (lane & 1), v);
+              }
+              if (lane == 0) ptx::sts32(gn_counters + acc * 4, 0.f);
+              __syncwarp();
+              __threadfence_block();
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       }
-      if (do_stats) flush();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
+    };
+    switch (p.mode) {
+      case EPI_STORE: run(std::integral_constant<int, EPI_STORE>{}); break;
+      case EPI_STATS: run(std::integral_constant<int, EPI_STATS>{}); break;
+      case EPI_RESID: run(std::integral_constant<int, EPI_RESID>{}); break;
+      case EPI_SNAKE: run(std::integral_constant<int, EPI_SNAKE>{}); break;
+      case EPI_MASK: run(std::integral_constant<int, EPI_MASK>{}); break;
+      default: run(std::integral_constant<int, EPI_ODE>{}); break;
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA exits while a peer may still multicast into / arrive on its smem
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -285,6 +285,91 @@ def c_stats_all():
             print(f"    utt{b} k={k} fused={float(res['fused'][site, b, k]):.6f} unfused={float(res['unfused'][site, b, k]):.6f}")
 
 
+def c_cluster():
+    """TMA-multicast cluster sizes 1/2/4: GEMM correctness vs the fp32-FMA kernel, then cfg2 decode time."""
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    for cl in (1, 2, 4):
+        os.environ["CFM_B200_CLUSTER"] = str(cl)
+        ora, m = _models(TINY, "euler", "bf16", 1)
+        m.refresh(torch.device("cuda", 0))
+        lib, h = m._lib, m._handle
+        g = torch.Generator().manual_seed(0)
+        worst = 0.0
+        for (M, N, K, taps) in [(128, 64, 64, 1), (300, 192, 256, 1), (1000, 384, 384, 3), (517, 160, 320, 3), (4096, 1536, 384, 1),
+                                (333, 100, 384, 1), (2048, 384, 1536, 1), (30144, 384, 384, 3), (30144, 1152, 384, 1)]:
+            a = torch.randn(M, K, generator=g).bfloat16().cuda()
+            w = (torch.randn(taps * N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+            shifts = [0] if taps == 1 else [-1, 0, 1]
+            sh = (C.c_int32 * taps)(*shifts)
+            d = [torch.full((M, N), float("nan"), device="cuda") for _ in range(2)]
+            for use_tc in (0, 1):
+                P.native.check(lib, h, lib.cfm_debug_gemm(h, a.data_ptr(), w.data_ptr(), d[use_tc].data_ptr(), M, N, K, taps, sh, use_tc, None))
+            torch.cuda.synchronize()
+            worst = max(worst, rel(d[1], d[0]))
+        print(f"[cluster {cl}] gemm tc-vs-simt worst rel = {worst:.3e}")
+        m.close()
+        cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+        m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16", flags=0).eval().cuda()
+        P.synthetic.fill_named_seed(m.estimator, 1234)
+        lengths = [938] * 32
+        mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+        ts = torch.linspace(0, 1, 11, device="cuda")
+        for _ in range(2):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"[cluster {cl}] cfg2 {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s finite={bool(torch.isfinite(out).all())}")
+        m.close()
+
+
+def c_gemmprof():
+    """Stand-alone GEMM timings (CUDA events, 20 reps) + CTA-0 role cycle counters for the cfg2 shapes."""
+    import torch
+    import matcha_tts_24k_b200 as P
+    ora, m = _models(TINY, "euler", "bf16", 1)
+    m.refresh(torch.device("cuda", 0))
+    lib, h = m._lib, m._handle
+    g = torch.Generator().manual_seed(0)
+    M = 30144
+    shapes = [("QKV bf16", 1152, 384, 1, 0), ("QKV f32out", 1152, 384, 1, 1), ("out-proj resid", 384, 384, 1, 2), ("out-proj f32", 384, 384, 1, 1),
+              ("out-proj bf16", 384, 384, 1, 0), ("conv2 f32", 384, 384, 3, 1), ("conv2 f32+stats", 384, 384, 3, 3), ("conv2 bf16", 384, 384, 3, 0), ("FF2 resid", 384, 1536, 1, 2),
+              ("FF2 bf16", 384, 1536, 1, 0), ("FF1 bf16", 1536, 384, 1, 0)]
+    for name, N, K, taps, mode in shapes:
+        a = torch.randn(M, K, generator=g).bfloat16().cuda()
+        w = (torch.randn(taps * N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+        shifts = [0] if taps == 1 else [-1, 0, 1]
+        sh = (C.c_int32 * taps)(*shifts)
+        d32 = torch.zeros(M, N, device="cuda")
+        d16 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+        call = lambda pr: P.native.check(lib, h, lib.cfm_debug_gemm_profile(h, a.data_ptr(), w.data_ptr(), d32.data_ptr(), d16.data_ptr(),
+                                                                        M, N, K, taps, sh, mode, pr, None))
+        for _ in range(3):
+            call(None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            call(None)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        call(prof.data_ptr())
+        torch.cuda.synchronize()
+        pr = prof.tolist()
+        fl = 2.0 * M * N * K * taps
+        print(f"[gemmprof {name:16s} N={N} K={K}x{taps}] {us:7.1f} us {fl/us/1e6:7.1f} TFLOP/s | tiles(cta0)={pr[8]} prod tot={pr[0]} wait_empty={pr[1]} | "
+              f"mma tot={pr[2]} wait_full={pr[3]} wait_tempty={pr[4]} | epi tot={pr[5]} wait_tfull={pr[6]}")
+
+
 CHECKS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("c_")}
 
 if __name__ == "__main__":
