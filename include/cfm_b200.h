@@ -106,6 +106,8 @@ int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches);
  * D[m,n] = sum_t sum_k A[m + shift[t], k] * W[t*N + n, k]; A (M x K), W (n_taps*N x K) bf16 device, D fp32. */
 int cfm_debug_gemm(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, int32_t M, int32_t N, int32_t K,
                    int32_t n_taps, const int32_t* shifts, int32_t use_tc, void* stream);
+/* Debug: every later attn_tc_kernel launch (direct launches only) writes CTA 0's cycle counters to prof_dev[0..16). */
+int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev);
 /* Debug: tensor-core GEMM in one epilogue mode (0 bf16 store, 1 fp32 store, 2 fp32 in-place residual add) with per-role
  * cycle counters of CTA 0 written to prof[0..16) (device memory); see csrc/cfm.cu for the slot meanings. */
 int cfm_debug_gemm_profile(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, void* d_bf16, int32_t M,

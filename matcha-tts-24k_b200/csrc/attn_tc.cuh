@@ -13,6 +13,7 @@
 #include <string>
 
 #include "attn.cuh"
+#include "gemm.cuh"
 #include "ptx.cuh"
 
 namespace cfm {
@@ -38,10 +39,82 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Row maximum of this thread's 64 raw scores (TMEM columns [taddr, taddr + 64)).  RAGGED: key index >= L is either the
+// virtual pad token (key == L, raw bias added) or outside the utterance (-inf).
+template <bool RAGGED>
+__device__ __forceinline__ float attn_rowmax(uint32_t taddr, int k0, int L, float raw_pad_bias) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t a[16], b[16];
+    ptx::tmem_ld16(taddr + c, a);
+    ptx::tmem_ld16(taddr + c + 16, b);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] = __uint_as_float((i + j) < 16 ? a[i + j] : b[i + j - 16]);
+        if (RAGGED) {
+          const int key = k0 + c + i + j;
+          t[j] = key < L ? t[j] : (key == L ? t[j] + raw_pad_bias : -INFINITY);
+        }
+      }
+      m0 = fmaxf(m0, t[0]), m1 = fmaxf(m1, t[1]), m2 = fmaxf(m2, t[2]), m3 = fmaxf(m3, t[3]);
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// P = exp2(s * scale_log2 - m) for this thread's 64 columns -> bf16 -> smem in the UMMA K-major 128B-swizzled layout
+// (16-byte chunk c of row r lives at chunk c ^ (r & 7)); returns the row's partial sum.
+template <bool RAGGED>
+__device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, int r, int k0, int L, float scale_log2,
+                                                float mnew, float pad_bias_log2) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t a[16], b[16];
+    ptx::tmem_ld16(taddr + c, a);
+    ptx::tmem_ld16(taddr + c + 16, b);
+    ptx::tmem_ld_wait();
+    float pv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
+      if (RAGGED) {
+        const int key = k0 + c + i;
+        t = key < L ? t : (key == L ? t + pad_bias_log2 : -INFINITY);
+      }
+      pv[i] = ex2_approx(t);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int chunk = (c >> 3) + g;
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[8 * g + 0], pv[8 * g + 1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[8 * g + 2], pv[8 * g + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[8 * g + 4], pv[8 * g + 5]);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[8 * g + 6], pv[8 * g + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = pk;
+    }
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttTable* __restrict__ utt,
-               const int4* __restrict__ work, bf16* __restrict__ out, long long ldo, float scale_log2) {
+               const int4* __restrict__ work, bf16* __restrict__ out, long long ldo, float scale_log2,
+               unsigned long long* prof) {
   using Cfg = AttnTcCfg;
+  const bool do_prof = prof != nullptr && blockIdx.x == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -96,23 +169,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 64, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + Cfg::OFF_Q), k_addr = ptx::smem_u32(smem + Cfg::OFF_K);
       const uint32_t v_addr = ptx::smem_u32(smem + Cfg::OFF_V), p_addr = ptx::smem_u32(smem + Cfg::OFF_P);
-      ptx::mbar_wait(bar_q, 0);
+      unsigned long long wq = 0, wk = 0, wp = 0, wv = 0;
+      const long long t_start = clock64();
+      mbar_wait_prof(bar_q, 0, do_prof, wq);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t ph = j & 1;
-        ptx::mbar_wait(bar_k, ph);
+        mbar_wait_prof(bar_k, ph, do_prof, wk);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           ptx::umma_bf16(tmem_s, ptx::umma_desc_sw128(q_addr + k * 32), ptx::umma_desc_sw128(k_addr + k * 32), idesc_s, k > 0);
         ptx::umma_commit(bar_s);
-        ptx::mbar_wait(bar_p, ph);  // P_j in smem, S_j and PV_{j-1} drained from TMEM
-        ptx::mbar_wait(bar_v, ph);
+        mbar_wait_prof(bar_p, ph, do_prof, wp);  // P_j in smem, S_j and PV_{j-1} drained from TMEM
+        mbar_wait_prof(bar_v, ph, do_prof, wv);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + (k >> 2) * (Cfg::QT * 128) + (k & 3) * 32),
                          ptx::umma_desc_sw128(v_addr + k * 2048), idesc_pv, k > 0);
         ptx::umma_commit(bar_pv);
+      }
+      if (do_prof) {
+        prof[0] = (unsigned long long)(clock64() - t_start), prof[1] = wq, prof[2] = wk, prof[3] = wp, prof[4] = wv;
+        prof[5] = (unsigned long long)n_tiles;
       }
     }
   } else {
@@ -127,70 +206,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
 #pragma unroll
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
     float mrun = -INFINITY, lrun = 0.f;
+    const bool sp = do_prof && warp == 2;
+    unsigned long long ws = 0, wbar = 0, wpv = 0;
+    const long long ts_start = clock64();
     uint8_t* p_row = smem + Cfg::OFF_P + hc * (Cfg::QT * 128) + r * 128;  // K-block hc of the P tile, row r
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const int k0 = j * Cfg::KT + hc * 64;
       const bool ragged = (k0 + 64 > L);  // this half holds the pad token and/or rows past this utterance
-      ptx::mbar_wait(bar_s, ph);
+      mbar_wait_prof(bar_s, ph, sp, ws);
       ptx::tc_fence_after();
-      // pass 1: maximum over this thread's 64 columns, then exchange with the partner half
-      float mt = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c, a);
-        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c + 16, b);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(i < 16 ? a[i] : b[i - 16]);
-          if (ragged) {
-            const int key = k0 + c + i;
-            t = key < L ? t : (key == L ? t + pad_bias / scale_log2 : -INFINITY);
-          }
-          mt = fmaxf(mt, t);
-        }
-      }
+      // The masking of ragged tiles (pad token, keys past the utterance) is hoisted out of the element loops: full tiles
+      // run a branch-free path.  Max and sum use 4 independent accumulators to break the dependency chains.
+      float mt;
+      if (!ragged) mt = attn_rowmax<false>(tmem_s + lane_off + hc * 64, k0, L, 0.f);
+      else mt = attn_rowmax<true>(tmem_s + lane_off + hc * 64, k0, L, pad_bias / scale_log2);
       red[hc * Cfg::QT + r] = mt;
-      named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
+      {
+        const long long tb = sp ? clock64() : 0;
+        named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
+        if (sp) wbar += (unsigned long long)(clock64() - tb);
+      }
       mt = fmaxf(mt, red[(hc ^ 1) * Cfg::QT + r]);
       const float mnew = fmaxf(mrun, mt * scale_log2);  // finite: key 0 of the first tile is always valid
       const float corr = ex2_approx(mrun - mnew);
-      float psum = 0.f;
-      // pass 2: P = exp2(s * c - m) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7))
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c, a);
-        ptx::tmem_ld16(tmem_s + lane_off + hc * 64 + c + 16, b);
-        ptx::tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
-          if (ragged) {
-            const int key = k0 + c + i;
-            t = key < L ? t : (key == L ? t + pad_bias : -INFINITY);
-          }
-          pv[i] = ex2_approx(t);
-          psum += pv[i];
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c >> 3) + g;
-          uint4 pk;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[8 * g + 0], pv[8 * g + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[8 * g + 2], pv[8 * g + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[8 * g + 4], pv[8 * g + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[8 * g + 6], pv[8 * g + 7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2);
-          pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = pk;
-        }
-      }
+      float psum;
+      if (!ragged) psum = attn_exp_store<false>(tmem_s + lane_off + hc * 64, p_row, r, k0, L, scale_log2, mnew, 0.f);
+      else psum = attn_exp_store<true>(tmem_s + lane_off + hc * 64, p_row, r, k0, L, scale_log2, mnew, pad_bias);
       lrun = lrun * corr + psum;
       mrun = mnew;
 #pragma unroll
@@ -198,7 +240,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
       ptx::tc_fence_before();
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::mbar_arrive(bar_p);
-      ptx::mbar_wait(bar_pv, ph);
+      mbar_wait_prof(bar_pv, ph, sp, wpv);
       ptx::tc_fence_after();
       {
         uint32_t a[16], b[16];
@@ -212,6 +254,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
         }
       }
     }
+    if (sp && lane == 0) prof[8] = (unsigned long long)(clock64() - ts_start), prof[9] = ws, prof[10] = wbar, prof[11] = wpv;
     ptx::tc_fence_before();
     // total row sum = both halves
     red[hc * Cfg::QT + r] = lrun;
@@ -255,7 +298,8 @@ inline int attn_tc_set_attr(std::string* err) {
 
 template <typename Enc>
 inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, int M, const UttTable* utt, const int4* work,
-                          int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err) {
+                          int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err,
+                          unsigned long long* prof = nullptr) {
   CUtensorMap tm;
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -269,7 +313,7 @@ inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, 
     return -2;
   }
   attn_tc_kernel<<<n_work, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, s>>>(tm, inner, utt, work, static_cast<bf16*>(out), ldo,
-                                                                           scale * 1.4426950408889634f);
+                                                                           scale * 1.4426950408889634f, prof);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);

@@ -89,6 +89,7 @@ struct Plan {
   float *xstate = nullptr, *vout = nullptr, *kbuf[3] = {nullptr, nullptr, nullptr};
   double* stats = nullptr;
   size_t stats_bytes = 0;
+  float2* gn_mr = nullptr;  // (mean, rstd) per site, utterance, group
   // activations per resolution (index 0 = full, 1 = half)
   void* xin = nullptr;
   int xin_ld = 0;
@@ -115,6 +116,7 @@ struct cfm_handle {
   int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
   int cluster = 2;                              // CTAs sharing one weight tile via TMA multicast
   long long launch_counter = 0;
+  unsigned long long* attn_prof = nullptr;  // debug: device buffer for attn_tc_kernel's CTA-0 cycle counters
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
   cudaStream_t own_stream = nullptr;
@@ -446,21 +448,23 @@ Res res_of(Plan* pl, int r) {
   return v;
 }
 
-int run_gn_apply(cfm_handle* h, const Res& R, const NormW& gn, const double* stats, const float* addvec, const float* resid,
+int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
                  float* out_f32, void* out_act, long long ld_act, cudaStream_t s) {
   if (h->stopped()) return 0;
-  h->launch_counter++;
+  h->launch_counter += 2;
   const int C = h->C();
-  const long long items = (long long)R.M * (C / 4);
+  const double* stats = pl->stats + (long long)site * pl->B * 16;
+  float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
+  gn_finalize_kernel<<<(pl->B * 8 + 127) / 128, 128, 0, s>>>(stats, gn.bias_gsum, R.utt, pl->B, C / 8, mr);
+  CK(cudaGetLastError());
+  const long long items = (long long)R.M * (C / 8);
   const int blocks = (int)((items + 255) / 256);
   if (h->bf)
-    gn_apply_kernel<bf16, false><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, R.utt, stats, gn.bias_gsum, gn.gamma,
-                                                        gn.beta, addvec, resid, C, out_f32, C, static_cast<bf16*>(out_act),
-                                                        ld_act);
+    gn_apply_kernel<bf16, false><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, mr, gn.gamma, gn.beta, addvec, resid, C,
+                                                        out_f32, C, static_cast<bf16*>(out_act), ld_act);
   else
-    gn_apply_kernel<float, true><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, R.utt, stats, gn.bias_gsum, gn.gamma,
-                                                        gn.beta, addvec, resid, C, out_f32, C, static_cast<float*>(out_act),
-                                                        ld_act);
+    gn_apply_kernel<float, true><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, mr, gn.gamma, gn.beta, addvec, resid, C,
+                                                        out_f32, C, static_cast<float*>(out_act), ld_act);
   CK(cudaGetLastError());
   return 0;
 }
@@ -506,7 +510,7 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
   const int I = h->inner(), D = h->cfg.head_dim;
   const float scale = 1.0f / sqrtf((float)D);
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
-  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err);
+  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err, h->attn_prof);
   if (h->bf) {
     if (D == 64)
       attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
@@ -537,10 +541,10 @@ int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const vo
     p.out_f32 = R.rres, p.ld_f32 = C;
     CKR(launch_gemm(h, p, true, s));
   }
-  CKR(run_gn_apply(h, R, w.gn1, pl->stats + (long long)site * pl->B * 16, tproj, nullptr, nullptr, R.hact, C, s));
+  CKR(run_gn_apply(h, pl, R, w.gn1, site, tproj, nullptr, nullptr, R.hact, C, s));
   site++;
   CKR(run_conv_stats(h, pl, R, R.hact, C, w.conv2, site, s));
-  CKR(run_gn_apply(h, R, w.gn2, pl->stats + (long long)site * pl->B * 16, nullptr, R.rres, R.X, nullptr, 0, s));
+  CKR(run_gn_apply(h, pl, R, w.gn2, site, nullptr, R.rres, R.X, nullptr, 0, s));
   site++;
   return 0;
 }
@@ -645,7 +649,7 @@ int emit_nfe(cfm_handle* h, Plan* pl, int nfe_index, const OdeStage& st, float* 
   }
   // final Block1D + 1x1 projection with the ODE update in the epilogue
   CKR(run_conv_stats(h, pl, R1, R1.hact, C, m.final_conv, site, s));
-  CKR(run_gn_apply(h, R1, m.final_gn, pl->stats + (long long)site * pl->B * 16, nullptr, nullptr, nullptr, R1.sin_, C, s));
+  CKR(run_gn_apply(h, pl, R1, m.final_gn, site, nullptr, nullptr, nullptr, R1.sin_, C, s));
   site++;
   {
     GemmParams p = gemm_base(R1.M, R1.sin_, C, R1.M, m.final_proj, nullptr, nullptr);
@@ -983,6 +987,7 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   const int n_sites = 2 * n_res + 1;
   pl->stats_bytes = (size_t)n_sites * batch * 16 * sizeof(double);
   CKR(dev_alloc(h, pl->allocs, reinterpret_cast<void**>(&pl->stats), pl->stats_bytes, &pl->bytes));
+  CKR(dev_alloc_t(h, pl->allocs, &pl->gn_mr, (size_t)n_sites * batch * 8, &pl->bytes));
   pl->xin_ld = roundup(h->cfg.in_channels, 64);
   CKR(dev_alloc(h, pl->allocs, &pl->xin, (size_t)pl->M1 * pl->xin_ld * es, &pl->bytes));
   for (int r = 0; r < 2; ++r) {
@@ -1142,6 +1147,12 @@ int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max
     return 0;
   }
   return fail(h, CFM_ERR_INVALID, "unknown debug buffer '%s'", name);
+}
+
+int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev) {
+  if (!h) return CFM_ERR_INVALID;
+  h->attn_prof = prof_dev;
+  return 0;
 }
 
 int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches) {

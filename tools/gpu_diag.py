@@ -370,6 +370,27 @@ def c_gemmprof():
               f"mma tot={pr[2]} wait_full={pr[3]} wait_tempty={pr[4]} | epi tot={pr[5]} wait_tfull={pr[6]}")
 
 
+def c_attnprof():
+    """CTA-0 cycle counters of attn_tc_kernel on cfg2 (first full-resolution attention of an estimator call)."""
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16", flags=1).eval().cuda()
+    P.synthetic.fill_named_seed(m.estimator, 1234)
+    lengths = [938] * 32
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+    m.estimator(z, mask, mu, torch.tensor(0.3))
+    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    m._lib.cfm_debug_attn_profile(m._handle, prof.data_ptr())
+    m._lib.cfm_debug_stop_after(m._handle, 12)  # memset, conv1, res, gn, conv2, gn, LN, QKV, attention
+    m.estimator(z, mask, mu, torch.tensor(0.3))
+    torch.cuda.synchronize()
+    p = prof.tolist()
+    print(f"[attnprof] tiles={p[5]} | mma thread: total={p[0]} wait_q={p[1]} wait_k={p[2]} wait_p={p[3]} wait_v={p[4]} | "
+          f"softmax warp: total={p[8]} wait_s={p[9]} wait_rowmax_barrier={p[10]} wait_pv={p[11]}")
+
+
 CHECKS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("c_")}
 
 if __name__ == "__main__":
