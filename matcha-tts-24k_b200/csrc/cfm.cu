@@ -114,7 +114,8 @@ struct cfm_handle {
   EncodeTiledFn encode = nullptr;
   int sm_count = 148;
   int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
-  int cluster = 2;                              // CTAs sharing one weight tile via TMA multicast
+  int cluster = 1;                              // 1-CTA kernel: CTAs sharing one weight tile via TMA multicast (no gain measured)
+  int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   long long launch_counter = 0;
   unsigned long long* attn_prof = nullptr;  // debug: device buffer for attn_tc_kernel's CTA-0 cycle counters
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
@@ -357,6 +358,30 @@ int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, co
 }
 
 template <int BN>
+int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
+                  cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN>;
+  const int m_pairs = (p.M + 255) / 256;
+  const int pair_tiles = m_pairs * ((p.N + BN - 1) / BN);
+  const int pairs = std::min(pair_tiles, h->max_clusters[2]);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(pairs * 2), cfg.blockDim = dim3(Cfg::THREADS), cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN>, a0, a1, w, p));
+  return 0;
+}
+
+template <int BN>
+int set_tc2_attr(cfm_handle* h) {
+  CK(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<BN>::SMEM_BYTES));
+  return 0;
+}
+
+template <int BN>
 int set_tc_attr(cfm_handle* h) {
   CK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
   if (BN == 192) {  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
@@ -397,8 +422,18 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     const int src = p.A[i] ? i : 0;
     CKR(make_tmap(h, &tmA[i], p.A[src], p.lda[src], p.a_rows[src], p.lda[src] * 2, 64, 128));
   }
-  p.cluster = h->cluster;
-  CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, bn / p.cluster));
+  // CTA-pair kernel where it measures faster: long reductions (k=3 convs, FF2); short-K GEMMs are epilogue-bound there.
+  p.pair = (h->pair_mode == 2 || (h->pair_mode == 1 && p.n_taps * p.K >= 1024)) && bn >= 128 ? 1 : 0;
+  p.cluster = p.pair ? 1 : h->cluster;
+  CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, p.pair ? bn / 2 : bn / p.cluster));
+  if (p.pair) {
+    switch (bn) {
+      case 128: return launch_tc2_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
+      case 160: return launch_tc2_bn<160>(h, tmA[0], tmA[1], tmW, p, s);
+      case 192: return launch_tc2_bn<192>(h, tmA[0], tmA[1], tmW, p, s);
+      default: return launch_tc2_bn<256>(h, tmA[0], tmA[1], tmW, p, s);
+    }
+  }
   switch (bn) {
     case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, p, s);
     case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
@@ -809,6 +844,7 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h->bf = cfg->precision == CFM_PREC_BF16;
   h->es = h->bf ? 2 : 4;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("CFM_B200_PAIR")) h->pair_mode = atoi(e);  // 0 never, 1 long-K GEMMs (default), 2 always
   if (const char* e = getenv("CFM_B200_CLUSTER")) {
     const int c = atoi(e);
     if (c == 1 || c == 2 || c == 4) h->cluster = c;
@@ -832,6 +868,10 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   r = r ? r : set_tc_attr<160>(h);
   r = r ? r : set_tc_attr<192>(h);
   r = r ? r : set_tc_attr<256>(h);
+  r = r ? r : set_tc2_attr<128>(h);
+  r = r ? r : set_tc2_attr<160>(h);
+  r = r ? r : set_tc2_attr<192>(h);
+  r = r ? r : set_tc2_attr<256>(h);
   r = r ? r : attn_tc_set_attr(&h->err);
   if (r) return bail(r);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }

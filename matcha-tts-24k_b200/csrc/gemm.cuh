@@ -74,6 +74,7 @@ struct GemmParams {
   float* kout;
   long long ld_k;
   int cluster;  // CTAs per cluster sharing one weight tile via TMA multicast (1, 2 or 4)
+  int pair;     // 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 per pair)
   unsigned long long* prof;  // debug: CTA 0 writes per-role cycle counters (see gemm_tc_kernel); nullptr = off
 };
 
@@ -388,7 +389,8 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 
 template <int MODE, int EPI_LD>
 __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int m0, int n, int lane, int info,
-                                          bool stats_uniform, bool do_stats, uint32_t warp_slots, int g_first) {
+                                          uint32_t valid_mask, uint32_t instat_mask, bool stats_uniform, bool do_stats,
+                                          uint32_t warp_slots, int g_first) {
   const int rs = lane >> 3, cg = lane & 7;
   const bool col_ok = n < p.N;  // N % 4 == 0: a lane's 4 columns are all inside or all outside
   if (!col_ok) n = 0;           // keep the lane in the shuffles below with harmless addresses, stores predicated off
@@ -418,18 +420,21 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
     const int r = it * 4 + rs;
     const int m = m0 + r;
     const float4 a = ptx::lds128(stg + (r * EPI_LD + cg * 4) * 4);
-    const int info_r = __shfl_sync(0xffffffffu, info, r);
+    int info_r = 0;
+    if constexpr (MODE == EPI_STATS) {
+      if (do_stats && !stats_uniform) info_r = __shfl_sync(0xffffffffu, info, r);  // utterance id per row: boundary warps only
+    }
     if (m >= p.M || !col_ok) continue;
     float x0 = a.x + b4.x, x1 = a.y + b4.y, x2 = a.z + b4.z, x3 = a.w + b4.w;
-    const bool valid = (info_r & ROW_VALID) != 0;
+    const bool valid = (valid_mask >> r) & 1u;
     if constexpr (MODE == EPI_STORE) {
       *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
     } else if constexpr (MODE == EPI_STATS) {
       *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
-      if (do_stats && (info_r & ROW_INSTAT)) {
+      if (do_stats && ((instat_mask >> r) & 1u)) {
         // Rows are sorted by utterance, so a lane sees a non-decreasing utterance id; in a warp that straddles a segment
         // boundary the running sums are flushed whenever the id changes (and once at the end), otherwise never here.
-        const int ur = info_r & ROW_UTT_MASK;
+        const int ur = stats_uniform ? 0 : (info_r & ROW_UTT_MASK);
         if (ur != cur_utt) {
           if (cur_utt >= 0 && !stats_uniform) {
             const long long o = ((long long)cur_utt * 8 + n / p.group_ch) * 2;
@@ -509,6 +514,144 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
         const long long o = ((long long)utt * 8 + n / p.group_ch) * 2;
         atomicAdd(p.stats + o, (double)gs);
         atomicAdd(p.stats + o + 1, (double)gss);
+      }
+    }
+  }
+}
+
+// bf16-output modes (STORE / SNAKE / MASK): 8 columns per lane (4 lanes cover 32 columns of a row, 8 rows per instruction),
+// one 16-byte store per lane and row.  Requires N % 8 == 0.
+template <int MODE, int EPI_LD>
+__device__ __forceinline__ void epi_block_wide(const GemmParams& p, uint32_t stg, int m0, int nblk, int lane, uint32_t valid_mask) {
+  const int rs = lane >> 2, cg = lane & 3;
+  const int n = nblk + cg * 8;
+  if (n >= p.N) return;  // no shuffles below: a lane may leave
+  float b[8], ea[8], ib[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = 0.f;
+  if (p.bias) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), t1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+    b[0] = t0.x, b[1] = t0.y, b[2] = t0.z, b[3] = t0.w, b[4] = t1.x, b[5] = t1.y, b[6] = t1.z, b[7] = t1.w;
+  }
+  if constexpr (MODE == EPI_SNAKE) {
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ea + n)), e1 = __ldg(reinterpret_cast<const float4*>(p.ea + n + 4));
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.ib + n)), i1 = __ldg(reinterpret_cast<const float4*>(p.ib + n + 4));
+    ea[0] = e0.x, ea[1] = e0.y, ea[2] = e0.z, ea[3] = e0.w, ea[4] = e1.x, ea[5] = e1.y, ea[6] = e1.z, ea[7] = e1.w;
+    ib[0] = i0.x, ib[1] = i0.y, ib[2] = i0.z, ib[3] = i0.w, ib[4] = i1.x, ib[5] = i1.y, ib[6] = i1.z, ib[7] = i1.w;
+  }
+  bf16* orow = reinterpret_cast<bf16*>(p.out_act) + (long long)(m0 + rs) * p.ld_act + n;
+  const long long ostep = 8 * p.ld_act;
+#pragma unroll
+  for (int it = 0; it < 4; ++it, orow += ostep) {
+    const int r = it * 8 + rs;
+    if (m0 + r >= p.M) break;  // rows increase with it
+    const float4 a0 = ptx::lds128(stg + (r * EPI_LD + cg * 8) * 4);
+    const float4 a1 = ptx::lds128(stg + (r * EPI_LD + cg * 8) * 4 + 16);
+    float x[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3], a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
+    if constexpr (MODE == EPI_SNAKE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float sn = ActIO<bf16>::fsin(x[i] * ea[i]);
+        x[i] = fmaf(sn * sn, ib[i], x[i]);
+      }
+    }
+    if constexpr (MODE == EPI_MASK) {
+      if (!((valid_mask >> r) & 1u)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+      }
+    }
+    const uint2 lo = pack4_bf16(x[0], x[1], x[2], x[3]), hi = pack4_bf16(x[4], x[5], x[6], x[7]);
+    *reinterpret_cast<uint4*>(orow) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// Epilogue of one 128-row x BN accumulator tile for one warp (TMEM lane quarter q = warp & 3; the two warps of a
+// quarter alternate over the 32-column blocks).  The next block's tcgen05.ld is issued before the current block's global
+// I/O so TMEM latency overlaps it.  Shared by the 1-CTA and the CTA-pair kernels.
+template <int BN, int MODE, int EPI_LD, int N_EPI_WARPS>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, uint32_t stg, int m0, int n0, int ewarp, int lane,
+                                              int acc, uint32_t gn_slots, uint32_t gn_counters) {
+  const int half = ewarp >> 2;
+  const int q = ewarp & 3;
+  const int info = load_row_info(p, m0 + lane);
+  const uint32_t valid_mask = __ballot_sync(0xffffffffu, (info & ROW_VALID) != 0);
+  const uint32_t instat_mask = __ballot_sync(0xffffffffu, (info & ROW_INSTAT) != 0);
+  bool do_stats = false, uniform = false;
+  uint32_t warp_slots = 0;
+  int tile_utt = 0, g_first = 0;
+  if constexpr (MODE == EPI_STATS) {
+    do_stats = p.fused_stats != 0;
+    const int utt = info & ROW_UTT_MASK;
+    if (do_stats) {
+      uniform = __all_sync(0xffffffffu, utt == __shfl_sync(0xffffffffu, utt, 0));
+      // If the 128 rows of the tile are one utterance (the common case) the sums are gathered per CTA in smem.
+      const int mt = m0 - q * 32;
+      const int u_lo = __ldg(p.row_info + min(mt, p.M - 1)) & ROW_UTT_MASK;
+      const int u_hi = __ldg(p.row_info + min(mt + 127, p.M - 1)) & ROW_UTT_MASK;
+      if (u_lo == u_hi && mt < p.M && (BN % p.group_ch) == 0 && p.row_mul == 1) {
+        warp_slots = gn_slots + ((acc * 8 + ewarp) * 16) * 4;
+        tile_utt = u_lo, g_first = n0 / p.group_ch;
+        uniform = true;  // rows past M carry no ROW_INSTAT flag and add nothing
+      }
+    }
+  }
+  constexpr bool WIDE = (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK);
+  const bool wide = WIDE && (p.N % 8 == 0);
+  uint32_t r0[16], r1[16];
+  if (half < BN / 32) {
+    ptx::tmem_ld16(taddr + half * 32, r0);
+    ptx::tmem_ld16(taddr + half * 32 + 16, r1);
+  }
+#pragma unroll 1
+  for (int blk = half; blk < BN / 32; blk += 2) {
+    const int c = blk * 32;
+    ptx::tmem_ld_wait();
+    const uint32_t srow = stg + lane * EPI_LD * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ptx::sts128(srow + i * 16, __uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]), __uint_as_float(r0[4 * i + 2]),
+                  __uint_as_float(r0[4 * i + 3]));
+      ptx::sts128(srow + 64 + i * 16, __uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]), __uint_as_float(r1[4 * i + 2]),
+                  __uint_as_float(r1[4 * i + 3]));
+    }
+    if (blk + 2 < BN / 32) {  // prefetch the next block's accumulators while this one goes out to global memory
+      ptx::tmem_ld16(taddr + c + 64, r0);
+      ptx::tmem_ld16(taddr + c + 64 + 16, r1);
+    }
+    __syncwarp();
+    if constexpr (WIDE) {
+      if (wide) epi_block_wide<MODE, EPI_LD>(p, stg, m0, n0 + c, lane, valid_mask);
+      else epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first);
+    } else {
+      epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first);
+    }
+    __syncwarp();
+  }
+  if constexpr (MODE == EPI_STATS) {
+    if (warp_slots) {  // the last of the 8 epilogue warps to finish this tile reduces and flushes (16 atomics / tile)
+      __syncwarp();
+      uint32_t old = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        old = ptx::atoms_add_u32(gn_counters + acc * 4, 1);
+      }
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == N_EPI_WARPS - 1) {
+        __threadfence_block();
+        if (lane < 16) {
+          double v = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) {
+            const uint32_t a = gn_slots + ((acc * 8 + w8) * 16 + lane) * 4;
+            v += (double)ptx::lds32(a);
+            ptx::sts32(a, 0.f);
+          }
+          if (v != 0.0) atomicAdd(p.stats + ((long long)tile_utt * 8 + g_first + (lane >> 1)) * 2 + (lane & 1), v);
+        }
+        if (lane == 0) ptx::sts32(gn_counters + acc * 4, 0.f);
+        __syncwarp();
+        __threadfence_block();
       }
     }
   }
@@ -690,75 +833,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         const int m0 = ((tile / n_tiles) * CL + crank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
-        const int info = load_row_info(p, m0 + lane);
-        bool do_stats = false, uniform = false;
-        uint32_t warp_slots = 0;
-        int tile_utt = 0, g_first = 0;
-        if constexpr (MODE == EPI_STATS) {
-          do_stats = p.fused_stats != 0;
-          const int utt = info & ROW_UTT_MASK;
-          if (do_stats) {
-            uniform = __all_sync(0xffffffffu, utt == __shfl_sync(0xffffffffu, utt, 0));
-            // If the 128 rows of the tile are one utterance (the common case) the sums are gathered per CTA in smem.
-            const int mt = m0 - q * 32;
-            const int u_lo = __ldg(p.row_info + min(mt, p.M - 1)) & ROW_UTT_MASK;
-            const int u_hi = __ldg(p.row_info + min(mt + Cfg::BM - 1, p.M - 1)) & ROW_UTT_MASK;
-            if (u_lo == u_hi && mt < p.M && (BN % p.group_ch) == 0 && p.row_mul == 1) {
-              warp_slots = gn_slots + ((acc * 8 + (warp - 4)) * 16) * 4;
-              tile_utt = u_lo, g_first = n0 / p.group_ch;
-              uniform = true;  // rows past M carry no ROW_INSTAT flag and add nothing
-            }
-          }
-        }
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int blk = half; blk < BN / 32; blk += 2) {
-          const int c = blk * 32;
-          uint32_t r0[16], r1[16];
-          ptx::tmem_ld16(taddr + c, r0);
-          ptx::tmem_ld16(taddr + c + 16, r1);
-          ptx::tmem_ld_wait();
-          const uint32_t srow = stg + lane * Cfg::EPI_LD * 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ptx::sts128(srow + i * 16, __uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]), __uint_as_float(r0[4 * i + 2]),
-                        __uint_as_float(r0[4 * i + 3]));
-            ptx::sts128(srow + 64 + i * 16, __uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]),
-                        __uint_as_float(r1[4 * i + 2]), __uint_as_float(r1[4 * i + 3]));
-          }
-          __syncwarp();
-          epi_block<MODE, Cfg::EPI_LD>(p, stg, m0, n0 + c + cg * 4, lane, info, uniform, do_stats, warp_slots, g_first);
-          __syncwarp();
-        }
-        if constexpr (MODE == EPI_STATS) {
-          if (warp_slots) {  // the last of the 8 epilogue warps to finish this tile reduces and flushes (16 atomics / tile)
-            __syncwarp();
-            uint32_t old = 0;
-            if (lane == 0) {
-              __threadfence_block();
-              old = ptx::atoms_add_u32(gn_counters + acc * 4, 1);
-            }
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == Cfg::N_EPI_WARPS - 1) {
-              __threadfence_block();
-              if (lane < 16) {
-                double v = 0.0;
-#pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) {
-                  const uint32_t a = gn_slots + ((acc * 8 + w8) * 16 + lane) * 4;
-                  v += (double)ptx::lds32(a);
-                  ptx::sts32(a, 0.f);
-                }
-                if (v != 0.0) atomicAdd(p.stats + ((long long)tile_utt * 8 + g_first + (lane >> 1)) * 2 + (lane & 1), v);
-              }
-              if (lane == 0) ptx::sts32(gn_counters + acc * 4, 0.f);
-              __syncwarp();
-              __threadfence_block();
-            }
-          }
-        }
+        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -780,6 +858,195 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs on neighbouring SMs compute one 256 x BN tile.  Each CTA loads the
+// A rows of its own 128-row half and HALF of the weight tile (BN/2 rows); the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256), which feeds both tensor cores from both shared memories, so every weight byte is
+// read from shared memory once per pair instead of once per CTA.  In the 1-CTA kernel TMA writes plus UMMA operand
+// reads ask for ~210 B/clk of shared-memory bandwidth at full MMA rate (the SM has 128): measured 55-60 % tensor
+// utilisation.  Here the demand is ~125-145 B/clk.
+//   full barrier   : leader's, count 1 (+ tx bytes of BOTH CTAs' loads, routed there by the .cta_group::2 TMA form)
+//   empty barrier  : one per CTA, count 1, signalled by the leader's tcgen05.commit multicast to both CTAs
+//   tmem-full      : one per CTA, count 1, same multicast commit
+//   tmem-empty     : leader's, count 16 = 8 epilogue warps x 2 CTAs (the follower's warps arrive remotely)
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MAX_SMEM = 227 * 1024;
+  static constexpr int CTRL_BYTES = 2048;
+  static constexpr int N_EPI_WARPS = 8;
+  static constexpr int EPI_LD = 36;
+  static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + CTRL_BYTES + EPI_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int THREADS = 128 + 32 * N_EPI_WARPS;
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64, 256]");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(Tc2Cfg<BN>::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();  // 0 = leader
+  const int m_pairs = (p.M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int n_tiles_total = m_pairs * n_tiles;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int kb_per_tap = p.K / Cfg::BK;
+  const int k_iters = p.n_taps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA0);
+    ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 2 * Cfg::N_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  const uint32_t gn_slots = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  const uint32_t gn_counters = gn_slots + 2 * 8 * 8 * 2 * 4;
+  if (warp == 3) {
+    for (int i = lane; i < 2 * 8 * 8 * 2 + 2; i += 32) ptx::sts32(gn_slots + i * 4, 0.f);
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // both CTAs' barriers and TMEM are set up before any cross-CTA traffic
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane per CTA) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const bool prof = p.prof != nullptr && blockIdx.x == 0;
+      unsigned long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int tile = pair_id; tile < n_tiles_total; tile += n_pairs) {
+        const int m0 = ((tile / n_tiles) * 2 + rank) * Cfg::BM, n0 = (tile % n_tiles) * BN + rank * (BN / 2);
+        for (int t = 0; t < p.n_taps; ++t) {
+          const GemmTap tap = p.taps[t];
+          const CUtensorMap* tmA = tap.a_src ? &tmA1 : &tmA0;
+          for (int kb = 0; kb < kb_per_tap; ++kb) {
+            mbar_wait_prof(&empty_bar[stage], phase ^ 1, prof, w_empty);
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            ptx::tma_load_2d_pair(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
+            ptx::tma_load_2d_pair(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+      if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * Cfg::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      const bool prof = p.prof != nullptr && blockIdx.x == 0;
+      unsigned long long w_full = 0, w_tempty = 0;
+      const long long t_start = clock64();
+      for (int tile = pair_id; tile < n_tiles_total; tile += n_pairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait_prof(&tempty_bar[acc], acc_phase ^ 1, prof, w_tempty);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait_prof(&full_bar[stage], phase, prof, w_full);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            ptx::umma_bf16_pair(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
+                                (it > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit_pair(&empty_bar[stage], 3);  // frees the stage in both CTAs
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        ptx::umma_commit_pair(&tfull_bar[acc], 3);  // accumulator ready in both CTAs
+      }
+      if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
+    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * 32 * Cfg::EPI_LD * 4;
+    auto run = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      const int q = warp & 3;
+      const int half = (warp - 4) >> 2;
+      const int cg = lane & 7;
+      int local = 0;
+      const bool prof = p.prof != nullptr && blockIdx.x == 0 && warp == 4;
+      unsigned long long w_tfull = 0;
+      const long long t_start = clock64();
+      for (int tile = pair_id; tile < n_tiles_total; tile += n_pairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        const int m0 = ((tile / n_tiles) * 2 + rank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
+        mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {  // the accumulator of BOTH CTAs must be drained before the leader's MMA thread reuses it
+          if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+        }
+      }
+      if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
+    };
+    switch (p.mode) {
+      case EPI_STORE: run(std::integral_constant<int, EPI_STORE>{}); break;
+      case EPI_STATS: run(std::integral_constant<int, EPI_STATS>{}); break;
+      case EPI_RESID: run(std::integral_constant<int, EPI_RESID>{}); break;
+      case EPI_SNAKE: run(std::integral_constant<int, EPI_SNAKE>{}); break;
+      case EPI_MASK: run(std::integral_constant<int, EPI_MASK>{}); break;
+      default: run(std::integral_constant<int, EPI_ODE>{}); break;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // neither CTA leaves while its partner may still touch its smem / TMEM / barriers
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -290,8 +290,10 @@ def c_cluster():
     import types
     import torch
     import matcha_tts_24k_b200 as P
-    for cl in (1, 2, 4):
+    for cl, pair in ((1, 0), (1, 1), (1, 2)):
         os.environ["CFM_B200_CLUSTER"] = str(cl)
+        os.environ["CFM_B200_PAIR"] = str(pair)
+        cl = f"{cl} pair={pair}"
         ora, m = _models(TINY, "euler", "bf16", 1)
         m.refresh(torch.device("cuda", 0))
         lib, h = m._lib, m._handle
