@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ode-steps", type=int, default=N_STEPS_ODE, help="Euler steps per decode (BASELINE config 5 sweeps 2/4/10/32)")
+    ap.add_argument("--spks", type=int, default=0, help="speaker-vector width S for upstream-style conditioning (config 5: 96)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,13 +177,14 @@ def main():
         T = 2 * ((max(all_lengths) + 1) // 2)
         lengths, scaling, job_frames = all_lengths, "weak", sum(all_lengths) * world
     cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
-    model = P.CFM(200, 100, cp, P.synthetic.PROD, precision=args.precision, flags=args.flags).eval()
+    model = P.CFM(200 + args.spks, 100, cp, P.synthetic.PROD, precision=args.precision, flags=args.flags).eval()
     P.synthetic.fill_named_seed(model.estimator, 1234)
     model = model.to(dev)
     mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1 + rank, T=T)
     mu_h, z_h = mu.pin_memory(), z.pin_memory()
     mu, mask, z = mu.to(dev), mask.to(dev), z.to(dev)
-    ts = torch.linspace(0, 1, N_STEPS_ODE + 1, device=dev)
+    ts = torch.linspace(0, 1, args.ode_steps + 1, device=dev)
+    spks = torch.randn(len(lengths), args.spks, generator=torch.Generator().manual_seed(3)).to(dev) if args.spks else None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -205,13 +208,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), out
 
-    dev_step = lambda: model.solve(z, ts, mu, mask, lengths=lengths)
-    host_step = lambda: model.solve_host(z_h, ts.cpu(), mu_h, lengths, device=dev)
-    for _ in range(args.warmup):
+    dev_step = lambda: model.solve(z, ts, mu, mask, lengths=lengths, spks=spks)
+    host_step = (lambda: model.solve_host(z_h, ts.cpu(), mu_h, lengths, device=dev)) if not args.spks else dev_step
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < args.warmup or time.perf_counter() - t_w < 1.5:  # >= W steps and >= 1.5 s: clocks and caches settled
         out = dev_step()
+        torch.cuda.synchronize(dev)
+        n_w += 1
     with ClockSampler(local_rank) as clk:
         ms_total, _, out = timed(dev_step, args.steps)
-    for _ in range(2):
+    for _ in range(3):
         host_step()
     _, wall_ms_e2e, out_h = timed(host_step, args.steps)
     if not bool(torch.isfinite(out).all()) or not bool(torch.isfinite(out_h).all()):
@@ -222,7 +229,7 @@ def main():
     value = job_frames / (ms_step * 1e-3)
     e2e_ms = wall_ms_e2e / args.steps
     pk = peaks()
-    flops = P.synthetic.algorithmic_flops(lengths, 384, N_STEPS_ODE)  # this rank's decode
+    flops = P.synthetic.algorithmic_flops(lengths, 384, args.ode_steps) + 8.0 * args.spks * 384 * sum(lengths) * args.ode_steps
     achieved = flops / (ms_step * 1e-3) / 1e12
     n_bytes = mu_h.numel() * 4
     line = {
@@ -230,12 +237,12 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": desc, "estimator": "prod C=384 H=6 d=64 n_blocks=2 mid=2 (37.03 M params, random init + N(0,0.1) 1-D)",
-                   "ode": "euler x10, one CUDA graph", "batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "t_pad": T,
+                   "ode": f"euler x{args.ode_steps}, one CUDA graph", "spks": args.spks, "batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "t_pad": T,
                    "rows_full": info["rows_full"], "l2": f"workspace {info['workspace_bytes'] / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
                    "parallelism": "utterance-sharded replicas, no collective" if world > 1 else "single GPU"},
         "rtf": (ms_step * 1e-3) / (job_frames * FRAME_SECONDS),
         "e2e": {"value": job_frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * n_bytes, "d2h_bytes_per_step": n_bytes, "api": "cfm_solve_host (C ABI, pinned host buffers)"},
+                "h2d_bytes_per_step": 2 * n_bytes, "d2h_bytes_per_step": n_bytes, "api": "cfm_solve_host (C ABI, pinned host buffers)" if not args.spks else "device-resident (no host-buffer entry with spks)"},
         "gpu_launches": int(info["kernels_per_solve"]) * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",

@@ -86,6 +86,12 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
  * moves them.  Asynchronous on `stream`. */
 int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* stream);
 
+/* Upstream Matcha-TTS speaker conditioning (the fork removed it: documentation/PROBLEMS.md:41-46; BASELINE config 5 names
+ * it): when the estimator was created with in_channels = 2 * out_channels + S, `spks` is a device fp32 (batch, S) matrix
+ * that the next cfm_solve / cfm_estimator broadcasts over time and concatenates after [x, mu] (upstream
+ * Decoder.forward(x, mask, mu, t, spks)).  The pointer must stay valid until that call has been enqueued. */
+int cfm_set_speakers(cfm_handle* h, const float* spks);
+
 /* Same with HOST buffers (pinned or pageable): H2D of mu and z, solve, D2H of out, then synchronises.
  * This is the call a non-PyTorch host (cgo / JNI / N-API) binds. */
 int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out);

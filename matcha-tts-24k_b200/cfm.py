@@ -140,9 +140,6 @@ class CFM(torch.nn.Module):
     def forward(self, mu, mask, n_timesteps, temperature: float = 1.0, spks=None, cond=None, lengths=None):
         """reference flow_matching.py:25-58.  ``temperature``/``spks``/``cond`` are the upstream Matcha-TTS superset;
         with their defaults this is exactly the fork's ``forward(mu, mask, n_timesteps)``."""
-        if spks is not None:
-            raise NotImplementedError("decoder speaker conditioning was removed from the fork "
-                                      "(documentation/PROBLEMS.md:41-46); not implemented in this round")
         g = torch.Generator(device=mu.device)
         g.manual_seed(42)
         noise = torch.randn(mu.shape, generator=g, device=mu.device, dtype=mu.dtype)
@@ -150,13 +147,22 @@ class CFM(torch.nn.Module):
             noise = noise * temperature
         z = mu + noise if self.use_mu_prior else noise
         t_span = torch.linspace(0, 1, n_timesteps + 1, device=mu.device)
-        return self.solve(z, t_span=t_span, mu=mu, mask=mask, lengths=lengths)
+        return self.solve(z, t_span=t_span, mu=mu, mask=mask, lengths=lengths, spks=spks)
 
     @torch.inference_mode()
-    def solve(self, x, t_span, mu, mask, lengths=None):
-        """reference flow_matching.py:60-63; ``x`` is the injected initial state z."""
+    def solve(self, x, t_span, mu, mask, lengths=None, spks=None):
+        """reference flow_matching.py:60-63; ``x`` is the injected initial state z.  ``spks`` (B, S): upstream-style
+        speaker conditioning, only for an estimator built with in_channels = 2*n_feats + S."""
         mu_, x_ = self._prep(mu), self._prep(x)
         B, F, T = mu_.shape
+        spk_dim = self._weights.cfg.in_channels - 2 * self._weights.cfg.out_channels
+        if (spks is None) != (spk_dim == 0):
+            raise ValueError(f"estimator has {spk_dim} speaker channels but spks is {'missing' if spks is None else 'given'}")
+        spks_ = None
+        if spks is not None:
+            spks_ = self._prep(spks)
+            if tuple(spks_.shape) != (B, spk_dim):
+                raise ValueError(f"spks must have shape ({B}, {spk_dim})")
         if x_.shape != mu_.shape or mask.shape[0] != B or mask.shape[-1] != T:
             raise ValueError("x, mu and mask disagree on (B, F, T)")
         if lengths is None:
@@ -165,6 +171,7 @@ class CFM(torch.nn.Module):
         lib, handle = self._ensure(mu_.device, [int(v) for v in lengths], T, ts, self.solver)
         out = torch.empty_like(mu_)
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        N.check(lib, handle, lib.cfm_set_speakers(handle, spks_.data_ptr() if spks_ is not None else None))
         N.check(lib, handle, lib.cfm_solve(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr(), stream))
         return out
 
@@ -176,13 +183,17 @@ class CFM(torch.nn.Module):
         B, F, T = mu_.shape
         ts = [float(v) for v in torch.as_tensor(t_span, dtype=torch.float32).tolist()]
         lib, handle = self._ensure(device, [int(v) for v in lengths], T, ts, self.solver)
-        out = torch.empty_like(mu_, pin_memory=mu_.is_pinned())
+        out = getattr(self, "_host_out", None)
+        if out is None or out.shape != mu_.shape or out.is_pinned() != mu_.is_pinned():
+            out = torch.empty_like(mu_, pin_memory=mu_.is_pinned())  # reused across calls: pinning is the slow part
+            object.__setattr__(self, "_host_out", out)
         N.check(lib, handle, lib.cfm_solve_host(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr()))
         return out
 
-    def _estimator_call(self, x, mask, mu, t):
+    def _estimator_call(self, x, mask, mu, t, spks=None):
         mu_, x_ = self._prep(mu), self._prep(x)
         B, F, T = mu_.shape
+        spks_ = self._prep(spks) if spks is not None else None
         tt = torch.as_tensor(t)
         if tt.numel() != 1:
             raise NotImplementedError("per-sample t (training, reference flow_matching.py:84-97) is not on this path")
@@ -190,6 +201,7 @@ class CFM(torch.nn.Module):
         lib, handle = self._ensure(mu_.device, lengths, T, [0.0, 1.0], "euler")
         v = torch.empty_like(mu_)
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        N.check(lib, handle, lib.cfm_set_speakers(handle, spks_.data_ptr() if spks_ is not None else None))
         N.check(lib, handle, lib.cfm_estimator(handle, x_.data_ptr(), mu_.data_ptr(), float(tt), v.data_ptr(), stream))
         return v
 

@@ -90,6 +90,7 @@ struct Plan {
   double* stats = nullptr;
   size_t stats_bytes = 0;
   float2* gn_mr = nullptr;  // (mean, rstd) per site, utterance, group
+  float *stage_mu = nullptr, *stage_z = nullptr, *stage_out = nullptr;  // cfm_solve_host device staging
   // activations per resolution (index 0 = full, 1 = half)
   void* xin = nullptr;
   int xin_ld = 0;
@@ -117,6 +118,7 @@ struct cfm_handle {
   int cluster = 1;                              // 1-CTA kernel: CTAs sharing one weight tile via TMA multicast (no gain measured)
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   long long launch_counter = 0;
+  const float* spks = nullptr;  // device (B, S) speaker vectors for the next pack (cfm_set_speakers); S = in_channels - 2 F
   unsigned long long* attn_prof = nullptr;  // debug: device buffer for attn_tc_kernel's CTA-0 cycle counters
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
@@ -746,6 +748,15 @@ int emit_pack(cfm_handle* h, Plan* pl, const float* x, const float* mu, cudaStre
     pack_rows_kernel<float><<<grid, block, 0, s>>>(mu, F, pl->T, pl->utt1, static_cast<float*>(pl->xin), pl->xin_ld, F, nullptr, 0, 1.f);
   }
   CK(cudaGetLastError());
+  const int S = h->cfg.in_channels - 2 * F;
+  if (S > 0) {
+    if (!h->spks) return fail(h, CFM_ERR_STATE, "this estimator has %d speaker channels: call cfm_set_speakers before the decode", S);
+    h->launch_counter++;
+    dim3 g2((max_rows * S + 255) / 256, pl->B);
+    if (h->bf) pack_speaker_kernel<bf16><<<g2, 256, 0, s>>>(h->spks, S, pl->utt1, static_cast<bf16*>(pl->xin), pl->xin_ld, 2 * F);
+    else pack_speaker_kernel<float><<<g2, 256, 0, s>>>(h->spks, S, pl->utt1, static_cast<float*>(pl->xin), pl->xin_ld, 2 * F);
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1083,19 +1094,16 @@ int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) {
   Plan* pl = h->plan;
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)pl->B * h->cfg.out_channels * pl->T;
-  float *dmu = nullptr, *dz = nullptr, *dout = nullptr;
-  CK(cudaMalloc(&dmu, n * 4));
-  CK(cudaMalloc(&dz, n * 4));
-  CK(cudaMalloc(&dout, n * 4));
-  int r = 0;
-  cudaError_t e = cudaMemcpyAsync(dmu, mu, n * 4, cudaMemcpyHostToDevice, h->own_stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dz, z, n * 4, cudaMemcpyHostToDevice, h->own_stream);
-  if (e == cudaSuccess) r = cfm_solve(h, dmu, dz, dout, h->own_stream);
-  if (e == cudaSuccess && r == 0) e = cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, h->own_stream);
-  if (e == cudaSuccess && r == 0) e = cudaStreamSynchronize(h->own_stream);
-  cudaFree(dmu), cudaFree(dz), cudaFree(dout);
-  if (r) return r;
-  if (e != cudaSuccess) return fail(h, CFM_ERR_CUDA, "cfm_solve_host: %s", cudaGetErrorString(e));
+  if (!pl->stage_mu) {  // device staging buffers live with the plan: no allocation on the per-call path
+    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_mu, n, &pl->bytes));
+    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_z, n, &pl->bytes));
+    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_out, n, &pl->bytes));
+  }
+  CK(cudaMemcpyAsync(pl->stage_mu, mu, n * 4, cudaMemcpyHostToDevice, h->own_stream));
+  CK(cudaMemcpyAsync(pl->stage_z, z, n * 4, cudaMemcpyHostToDevice, h->own_stream));
+  CKR(cfm_solve(h, pl->stage_mu, pl->stage_z, pl->stage_out, h->own_stream));
+  CK(cudaMemcpyAsync(out, pl->stage_out, n * 4, cudaMemcpyDeviceToHost, h->own_stream));
+  CK(cudaStreamSynchronize(h->own_stream));
   return 0;
 }
 
@@ -1187,6 +1195,12 @@ int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max
     return 0;
   }
   return fail(h, CFM_ERR_INVALID, "unknown debug buffer '%s'", name);
+}
+
+int cfm_set_speakers(cfm_handle* h, const float* spks_dev) {
+  if (!h) return CFM_ERR_INVALID;
+  h->spks = spks_dev;
+  return 0;
 }
 
 int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev) {

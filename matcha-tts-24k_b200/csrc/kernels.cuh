@@ -91,6 +91,19 @@ __global__ void unpack_rows_kernel(const float* __restrict__ state, long long ld
   }
 }
 
+// Upstream-style speaker conditioning: spks (B, S) broadcast over the valid frames of each utterance into columns
+// [col0, col0 + S) of the token-major estimator input (rows t >= L stay zero, as x * mask does in the reference).
+template <typename T>
+__global__ void pack_speaker_kernel(const float* __restrict__ spks, int S, const UttTable* __restrict__ utt,
+                                    T* __restrict__ dst, long long ld, int col0) {
+  const int b = blockIdx.y;
+  const UttTable u = utt[b];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = idx / S, s_ = idx % S;
+  if (t >= u.rows) return;
+  ActIO<T>::st(dst + (long long)(u.start + t) * ld + col0 + s_, t < u.len ? spks[(long long)b * S + s_] : 0.f);
+}
+
 // ---------------------------------------------------------------------------------- GroupNorm
 // Stand-alone statistics pass (fp32 mode and the debug path; the tensor-core GEMM fuses this into its epilogue).
 __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M, int C, int group_ch,

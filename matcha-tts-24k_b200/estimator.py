@@ -143,9 +143,9 @@ class EstimatorWeights(nn.Module):
                 else:
                     nn.init.zeros_(p)
 
-    def forward(self, x, mask, mu, t):
+    def forward(self, x, mask, mu, t, spks=None):
         """One estimator evaluation v = f(x, mask, mu, t) on the GPU (reference decoder.py:359-426).
         Inference only: there is no autograd path through the CUDA library."""
         if self._owner is None:
             raise RuntimeError("EstimatorWeights is not attached to a CFM")
-        return self._owner[0]._estimator_call(x, mask, mu, t)
+        return self._owner[0]._estimator_call(x, mask, mu, t, spks)

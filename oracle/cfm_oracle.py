@@ -253,10 +253,14 @@ class Decoder(nn.Module):
             x = blk(x, bias)
         return x.transpose(1, 2)
 
-    def forward(self, x, mask, mu, t):
-        """ref: decoder.py:359-426."""
+    def forward(self, x, mask, mu, t, spks=None):
+        """ref: decoder.py:359-426.  ``spks`` (B, S) is NOT in the fork (removed, documentation/PROBLEMS.md:41-46): it restates
+        upstream Matcha-TTS, where the speaker vector is broadcast over time and concatenated after [x, mu]
+        (in_channels = 2 F + S) -- BASELINE config 5 names it."""
         temb = self.time_mlp(sinusoidal_embedding(t, self.in_channels).to(x.dtype))
         x = torch.cat([x, mu], dim=1)
+        if spks is not None:
+            x = torch.cat([x, spks.unsqueeze(-1).expand(-1, -1, x.shape[-1])], dim=1)
         skips, masks = [], [mask]
         for res, blocks, tail in self.down_blocks:
             m = masks[-1]
@@ -327,9 +331,9 @@ class CFM(nn.Module):
         return self.solve(z, t_span=t_span, mu=mu, mask=mask)
 
     @torch.inference_mode()
-    def solve(self, x, t_span, mu, mask):
+    def solve(self, x, t_span, mu, mask, spks=None):
         """ref: flow_matching.py:60-63 + ode_solver_wrapper.py:11-16."""
-        return odeint_fixed_grid(lambda t, y: self.estimator(y, mask, mu, t), x, t_span.to(x.dtype), self.solver)
+        return odeint_fixed_grid(lambda t, y: self.estimator(y, mask, mu, t, spks), x, t_span.to(x.dtype), self.solver)
 
     def compute_loss(self, x1, mask, mu):
         """ref: flow_matching.py:65-107."""

@@ -105,6 +105,26 @@ def test_prod_config_mixed_lengths(precision):
     check(out, ref, precision, "prod C=384 mixed lengths, euler/4")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_upstream_style_speaker_conditioning(precision):
+    """BASELINE config 5: spks (B, S) broadcast over time and concatenated after [x, mu] (upstream Matcha-TTS; the fork
+    removed it, so the oracle side is a restatement of upstream behaviour, not of /root/reference)."""
+    S = 16
+    ora = O.CFM(200 + S, 100, cfm_params("euler"), TINY64).eval()
+    syn.fill_named_seed(ora.estimator, 77)
+    m = P.CFM(200 + S, 100, cfm_params("euler"), TINY64, precision=precision).eval()
+    m.estimator.load_state_dict(ora.estimator.state_dict())
+    m = m.cuda()
+    mu, mask, z, _ = syn.make_inputs([90, 41, 128], seed=6, T=128)
+    spks = torch.randn(3, S, generator=torch.Generator().manual_seed(1))
+    ts = torch.linspace(0, 1, 4)
+    ref = ora.solve(z, ts, mu, mask, spks)
+    out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda(), spks=spks.cuda())
+    check(out, ref, precision, "spks conditioning")
+    with pytest.raises(ValueError):
+        m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
+
+
 def test_forward_seed42_path_and_caller_context():
     """reference flow_matching.py:25-58 via the call pattern of inference.py:233-238 (inference_mode + fp16 autocast)."""
     ora, m = pair(TINY64, "euler", "fp32")
