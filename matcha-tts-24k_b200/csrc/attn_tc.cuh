@@ -10,6 +10,7 @@
 // The per-key bias implements the reference's additive float mask in the packed formulation (attn.cuh header).
 #pragma once
 #include <cuda.h>
+#include <cstring>
 #include <string>
 
 #include "attn.cuh"
@@ -123,7 +124,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
   float* red = reinterpret_cast<float*>(smem + Cfg::OFF_RED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int4 w = work[blockIdx.x];
+  ptx::pdl_launch_dependents();
+  const int4 w = work[blockIdx.x];  // plan-constant tables: safe to read before pdl_wait
   const UttTable u = utt[w.x];
   const int head = w.y, q0 = w.z;
   const int L = u.len, nk = u.len + 1;
@@ -149,6 +151,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+  ptx::pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
@@ -299,7 +302,7 @@ inline int attn_tc_set_attr(std::string* err) {
 template <typename Enc>
 inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, int M, const UttTable* utt, const int4* work,
                           int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err,
-                          unsigned long long* prof = nullptr) {
+                          unsigned long long* prof = nullptr, bool pdl = false) {
   CUtensorMap tm;
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -312,9 +315,15 @@ inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, 
     *err = "cuTensorMapEncodeTiled failed for the attention QKV map";
     return -2;
   }
-  attn_tc_kernel<<<n_work, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, s>>>(tm, inner, utt, work, static_cast<bf16*>(out), ldo,
-                                                                           scale * 1.4426950408889634f, prof);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(n_work), cfg.blockDim = dim3(AttnTcCfg::THREADS), cfg.dynamicSmemBytes = AttnTcCfg::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel, tm, inner, utt, work, static_cast<bf16*>(out), ldo,
+                                     scale * 1.4426950408889634f, prof);
   if (e != cudaSuccess) {
     *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);
     return -2;

@@ -13,6 +13,7 @@
 #include <map>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/cfm_b200.h"
@@ -116,6 +117,8 @@ struct cfm_handle {
   int sm_count = 148;
   int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
   int cluster = 1;                              // 1-CTA kernel: CTAs sharing one weight tile via TMA multicast (no gain measured)
+  int pdl = 0;                                  // programmatic dependent launch between the kernels of a decode (CFM_B200_PDL=1);
+                                                // measured neutral on cfg1/cfg2, so off by default
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   long long launch_counter = 0;
   const float* spks = nullptr;  // device (B, S) speaker vectors for the next pack (cfm_set_speakers); S = in_channels - 2 F
@@ -340,6 +343,31 @@ int pick_bn(int N) {
   return 192;
 }
 
+// Kernel launch with optional cluster dimension and the programmatic-dependent-launch attribute (PDL): the kernel may be
+// scheduled while its predecessor in the stream is still draining; it calls griddepcontrol.wait before touching memory.
+template <typename... KArgs, typename... Args>
+int launch_ex(cfm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster,
+              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (h->pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return 0;
+}
+
 template <int BN>
 int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
                  cudaStream_t s) {
@@ -348,15 +376,7 @@ int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, co
   const int m_super = ((p.M + 127) / 128 + CL - 1) / CL;
   const int super_tiles = m_super * ((p.N + BN - 1) / BN);
   const int clusters = std::min(super_tiles, h->max_clusters[CL]);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(clusters * CL), cfg.blockDim = dim3(Cfg::THREADS), cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, a0, a1, w, p));
-  return 0;
+  return launch_ex(h, gemm_tc_kernel<BN>, dim3(clusters * CL), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, CL, a0, a1, w, p);
 }
 
 template <int BN>
@@ -366,15 +386,7 @@ int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, c
   const int m_pairs = (p.M + 255) / 256;
   const int pair_tiles = m_pairs * ((p.N + BN - 1) / BN);
   const int pairs = std::min(pair_tiles, h->max_clusters[2]);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(pairs * 2), cfg.blockDim = dim3(Cfg::THREADS), cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN>, a0, a1, w, p));
-  return 0;
+  return launch_ex(h, gemm_tc2_kernel<BN>, dim3(pairs * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 2, a0, a1, w, p);
 }
 
 template <int BN>
@@ -488,22 +500,17 @@ Res res_of(Plan* pl, int r) {
 int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
                  float* out_f32, void* out_act, long long ld_act, cudaStream_t s) {
   if (h->stopped()) return 0;
-  h->launch_counter += 2;
+  h->launch_counter++;
   const int C = h->C();
   const double* stats = pl->stats + (long long)site * pl->B * 16;
-  float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
-  gn_finalize_kernel<<<(pl->B * 8 + 127) / 128, 128, 0, s>>>(stats, gn.bias_gsum, R.utt, pl->B, C / 8, mr);
-  CK(cudaGetLastError());
-  const long long items = (long long)R.M * (C / 8);
-  const int blocks = (int)((items + 255) / 256);
+  const int blocks = (R.M + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
   if (h->bf)
-    gn_apply_kernel<bf16, false><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, mr, gn.gamma, gn.beta, addvec, resid, C,
-                                                        out_f32, C, static_cast<bf16*>(out_act), ld_act);
-  else
-    gn_apply_kernel<float, true><<<blocks, 256, 0, s>>>(R.hraw, C, R.M, C, C / 8, R.info, mr, gn.gamma, gn.beta, addvec, resid, C,
-                                                        out_f32, C, static_cast<float*>(out_act), ld_act);
-  CK(cudaGetLastError());
-  return 0;
+    return launch_ex(h, gn_apply_kernel<bf16, false>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
+                     (const int*)R.info, (const UttTable*)R.utt, stats, (const double*)gn.bias_gsum, (const float*)gn.gamma,
+                     (const float*)gn.beta, addvec, resid, (long long)C, out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
+  return launch_ex(h, gn_apply_kernel<float, true>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
+                   (const int*)R.info, (const UttTable*)R.utt, stats, (const double*)gn.bias_gsum, (const float*)gn.gamma,
+                   (const float*)gn.beta, addvec, resid, (long long)C, out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
 }
 
 // Conv k=3 (+bias) -> fp32 raw output + GroupNorm statistics for site `site`.
@@ -534,11 +541,10 @@ int run_layernorm(cfm_handle* h, const Res& R, const NormW& ln, cudaStream_t s) 
   const int C = h->C();
   const int blocks = (R.M * 32 + 255) / 256;
   if (h->bf)
-    layernorm_kernel<bf16, 16><<<blocks, 256, 0, s>>>(R.X, C, R.M, C, ln.gamma, ln.beta, static_cast<bf16*>(R.Xn), C);
-  else
-    layernorm_kernel<float, 16><<<blocks, 256, 0, s>>>(R.X, C, R.M, C, ln.gamma, ln.beta, static_cast<float*>(R.Xn), C);
-  CK(cudaGetLastError());
-  return 0;
+    return launch_ex(h, layernorm_kernel<bf16, 16>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.X, (long long)C, R.M, C,
+                     (const float*)ln.gamma, (const float*)ln.beta, static_cast<bf16*>(R.Xn), (long long)C);
+  return launch_ex(h, layernorm_kernel<float, 16>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.X, (long long)C, R.M, C,
+                   (const float*)ln.gamma, (const float*)ln.beta, static_cast<float*>(R.Xn), (long long)C);
 }
 
 int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
@@ -547,7 +553,7 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
   const int I = h->inner(), D = h->cfg.head_dim;
   const float scale = 1.0f / sqrtf((float)D);
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
-  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err, h->attn_prof);
+  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err, h->attn_prof, h->pdl != 0);
   if (h->bf) {
     if (D == 64)
       attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
@@ -855,6 +861,7 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h->bf = cfg->precision == CFM_PREC_BF16;
   h->es = h->bf ? 2 : 4;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("CFM_B200_PDL")) h->pdl = atoi(e) != 0;
   if (const char* e = getenv("CFM_B200_PAIR")) h->pair_mode = atoi(e);  // 0 never, 1 long-K GEMMs (default), 2 always
   if (const char* e = getenv("CFM_B200_CLUSTER")) {
     const int c = atoi(e);

@@ -88,13 +88,9 @@ template <> struct ActIO<float> {
 template <> struct ActIO<bf16> {
   static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
-  // Cody-Waite reduction to [-pi, pi] then MUFU.SIN; the result is rounded to bf16 anyway.
-  static __device__ __forceinline__ float fsin(float x) {
-    float k = rintf(x * 0.15915494309189535f);
-    float r = fmaf(k, -6.2831854820251465f, x);
-    r = fmaf(k, 1.7484555e-7f, r);
-    return __sinf(r);
-  }
+  // sin.approx = (x / 2pi) -> MUFU.SIN, which reduces the range itself; absolute error ~ |x| * 4e-7, far below the
+  // bf16 rounding of the result for the arguments SnakeBeta sees (|h * e^alpha| up to a few hundred).
+  static __device__ __forceinline__ float fsin(float x) { return __sinf(x); }
 };
 
 template <typename T, int NV>
@@ -705,6 +701,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   // Cluster of CL CTAs = CL consecutive m-tiles of one n-tile ("super-tile"); every CTA of a cluster walks the same
   // super-tile list in lock step (a CTA whose m-tile lies past M still runs: its loads are zero-filled, stores predicated).
   const int CL = p.cluster;
@@ -749,6 +746,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (CL > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -906,6 +904,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   const int rank = (int)ptx::cluster_ctarank();  // 0 = leader
   const int m_pairs = (p.M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -944,6 +943,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   ptx::cluster_sync_all();  // both CTAs' barriers and TMEM are set up before any cross-CTA traffic
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one lane per CTA) =====================

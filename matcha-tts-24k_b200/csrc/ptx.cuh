@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: lets the next kernel of the stream (launched with the programmatic-serialization attribute) be
+// scheduled while this grid is still running; wait: blocks until every prerequisite grid has completed and its memory
+// is visible.  Everything a kernel does before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch, reads of
+// plan-constant tables) overlaps the tail of the previous kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- explicit shared-memory vector access
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
