@@ -1,12 +1,13 @@
 // Tensor-core flash attention for sm_100a (bf16, head_dim 64): softmax(Q K^T d^-1/2 + key_bias) V per (utterance, head).
 //
-// One CTA per (utterance, head, 128-query tile); 320 threads = TMA warp, MMA warp, 8 softmax warps (two threads per
-// query row, each owning half of the key columns and half of the output columns).  Per 128-key tile:
-//     S  = Q K^T      tcgen05.mma  M128 N128 K64   (Q, K tiles K-major, 128B-swizzled by TMA)    -> TMEM cols [0,128)
-//     P  = exp2(...)  tcgen05.ld S -> registers -> online softmax -> bf16 P written to smem in the UMMA K-major layout
-//     PV = P V        tcgen05.mma  M128 N64 K128   (V tile MN-major straight from TMA)            -> TMEM cols [128,192)
-//     O  = O*corr + PV in registers (tcgen05.ld)
-// Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// One CTA per (utterance, head, 128-query tile); 192 threads = TMA warp, MMA warp, 4 softmax warps (one query row per
+// thread).  Keys are processed in 64-key tiles through a software pipeline:
+//     S_j  = Q K_j^T    tcgen05.mma M128 N64 K64  (Q, K tiles K-major, 128B-swizzled by TMA)  -> TMEM S[j & 1]
+//     P_j  = exp2(...)  tcgen05.ld S_j -> registers -> online softmax -> bf16 P_j in smem P[j & 1] (UMMA K-major layout)
+//     PV_j = P_j V_j    tcgen05.mma M128 N64 K64  (V tile MN-major straight from TMA)         -> TMEM PV
+//     O   += PV_{j-1}   consumed one iteration late, in registers (packed fp32x2)
+// S, P, K and V are double-buffered, so S_{j+1} is computed while the softmax of tile j runs and the softmax warps never
+// wait on an MMA issued in the same iteration.  Two CTAs per SM (80 KB smem, 256 TMEM columns each).
 // The per-key bias implements the reference's additive float mask in the packed formulation (attn.cuh header).
 #pragma once
 #include <cuda.h>
@@ -20,15 +21,14 @@
 namespace cfm {
 
 struct AttnTcCfg {
-  static constexpr int D = 64, QT = 128, KT = 128;
+  static constexpr int D = 64, QT = 128, KT = 64;
   static constexpr int Q_BYTES = QT * D * 2, K_BYTES = KT * D * 2, V_BYTES = KT * D * 2, P_BYTES = QT * KT * 2;
-  static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;         // 6 mbarriers + TMEM slot (64 B)
-  static constexpr int OFF_RED = OFF_BAR + 64;            // [2][128] floats: row max / row sum exchange between column halves
-  static constexpr int SMEM_BYTES = OFF_RED + 2 * QT * 4 + 1024;
-  static constexpr int N_SOFTMAX_WARPS = 8;
+  static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + 2 * K_BYTES, OFF_P = OFF_V + 2 * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;  // 11 mbarriers + TMEM slot (128 B)
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int N_SOFTMAX_WARPS = 4;
   static constexpr int THREADS = 64 + 32 * N_SOFTMAX_WARPS;
-  static constexpr int TMEM_COLS = 256;
+  static constexpr int TMEM_COLS = 256;  // S[2] at columns 0 / 64, PV at column 128
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -36,8 +36,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+
+// Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) and the 3-input maximum (FMNMX3): halve the
+// instruction count of the softmax inner loops, which are issue-bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // Row maximum of this thread's 64 raw scores (TMEM columns [taddr, taddr + 64)).  RAGGED: key index >= L is either the
@@ -62,7 +89,7 @@ __device__ __forceinline__ float attn_rowmax(uint32_t taddr, int k0, int L, floa
           t[j] = key < L ? t[j] : (key == L ? t[j] + raw_pad_bias : -INFINITY);
         }
       }
-      m0 = fmaxf(m0, t[0]), m1 = fmaxf(m1, t[1]), m2 = fmaxf(m2, t[2]), m3 = fmaxf(m3, t[3]);
+      m0 = max3(m0, t[0], t[1]), m1 = max3(m1, t[2], t[3]);
     }
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
@@ -74,6 +101,7 @@ template <bool RAGGED>
 __device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, int r, int k0, int L, float scale_log2,
                                                 float mnew, float pad_bias_log2) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  f32x2 acc01 = pack2(0.f, 0.f), acc23 = pack2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < 64; c += 32) {
     uint32_t a[16], b[16];
@@ -81,17 +109,28 @@ __device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, 
     ptx::tmem_ld16(taddr + c + 16, b);
     ptx::tmem_ld_wait();
     float pv[32];
+    if constexpr (!RAGGED) {
+      const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-mnew, -mnew);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
-      if (RAGGED) {
+      for (int i = 0; i < 32; i += 2) {
+        const f32x2 t2 = fma2(pack2(__uint_as_float(i < 16 ? a[i] : b[i - 16]), __uint_as_float(i < 16 ? a[i + 1] : b[i - 15])), sc2, nm2);
+        float t0, t1;
+        unpack2(t2, t0, t1);
+        pv[i] = ex2_approx(t0), pv[i + 1] = ex2_approx(t1);
+        if ((i & 2) == 0) acc01 = add2(acc01, pack2(pv[i], pv[i + 1]));
+        else acc23 = add2(acc23, pack2(pv[i], pv[i + 1]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
         const int key = k0 + c + i;
         t = key < L ? t : (key == L ? t + pad_bias_log2 : -INFINITY);
+        pv[i] = ex2_approx(t);
       }
-      pv[i] = ex2_approx(t);
-    }
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
+      for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int chunk = (c >> 3) + g;
@@ -107,21 +146,26 @@ __device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, 
       *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = pk;
     }
   }
+  if constexpr (!RAGGED) {
+    const f32x2 t = add2(acc01, acc23);
+    unpack2(t, s0, s1);
+    return s0 + s1;
+  }
   return (s0 + s1) + (s2 + s3);
 }
 
 __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttTable* __restrict__ utt,
-               const int4* __restrict__ work, bf16* __restrict__ out, long long ldo, float scale_log2,
-               unsigned long long* prof) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int inner,
+               const UttTable* __restrict__ utt, const int4* __restrict__ work, bf16* __restrict__ out, long long ldo,
+               float scale_log2, unsigned long long* prof) {
   using Cfg = AttnTcCfg;
   const bool do_prof = prof != nullptr && blockIdx.x == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t *bar_q = bars + 0, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_p = bars + 4, *bar_pv = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* red = reinterpret_cast<float*>(smem + Cfg::OFF_RED);
+  // Every barrier is per buffer (index j & 1): a waiter can then never be more than one phase behind its barrier.
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 3, *bar_s = bars + 5, *bar_p = bars + 7, *bar_pv = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ptx::pdl_launch_dependents();
@@ -133,13 +177,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
   const int row0 = u.start;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_qkv);
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_kv);
     ptx::mbar_init(bar_q, 1);
-    ptx::mbar_init(bar_k, 1);
-    ptx::mbar_init(bar_v, 1);
-    ptx::mbar_init(bar_s, 1);
-    ptx::mbar_init(bar_p, 32 * Cfg::N_SOFTMAX_WARPS);
-    ptx::mbar_init(bar_pv, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_k + i, 1);
+      ptx::mbar_init(bar_v + i, 1);
+      ptx::mbar_init(bar_s + i, 1);
+      ptx::mbar_init(bar_p + i, 32 * Cfg::N_SOFTMAX_WARPS);
+      ptx::mbar_init(bar_pv + i, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -150,47 +197,61 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+  const uint32_t tmem_pv = tmem_base + 128;
   ptx::pdl_wait();
 
+  // Software pipeline over 64-key tiles j (buffer b = j & 1, use count u = j >> 1):
+  //   tensor core : S_0, S_1, [P_0] PV_0, S_2, [P_1] PV_1, S_3, ...   S_{j+2} reuses S[b] as soon as softmax_j has read S_j
+  //   softmax     : wait S_j -> max -> P_j = exp2(...) -> smem P[b] -> O += PV_{j-1} (finished long ago), O *= corr -> arrive P_j
+  // so the softmax warps never wait on an MMA issued in the same iteration.
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_qkv, bar_q, head * Cfg::D, row0 + q0);
+      ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_q, bar_q, head * Cfg::D, row0 + q0);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j > 0) ptx::mbar_wait(bar_s, (j - 1) & 1);  // S_{j-1} complete: K buffer free
-        ptx::mbar_expect_tx(bar_k, Cfg::K_BYTES);
-        ptx::tma_load_2d(smem + Cfg::OFF_K, &tm_qkv, bar_k, inner + head * Cfg::D, row0 + j * Cfg::KT);
-        if (j > 0) ptx::mbar_wait(bar_pv, (j - 1) & 1);  // PV_{j-1} complete: V buffer free
-        ptx::mbar_expect_tx(bar_v, Cfg::V_BYTES);
-        ptx::tma_load_2d(smem + Cfg::OFF_V, &tm_qkv, bar_v, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+        const int b = j & 1;
+        const uint32_t prev = ((j >> 1) - 1) & 1;  // parity of the previous use of buffer b
+        if (j >= 2) ptx::mbar_wait(bar_s + b, prev);  // S_{j-2} complete: K[b] free
+        ptx::mbar_expect_tx(bar_k + b, Cfg::K_BYTES);
+        ptx::tma_load_2d(smem + Cfg::OFF_K + b * Cfg::K_BYTES, &tm_kv, bar_k + b, inner + head * Cfg::D, row0 + j * Cfg::KT);
+        if (j >= 2) ptx::mbar_wait(bar_pv + b, prev);  // PV_{j-2} complete: V[b] free
+        ptx::mbar_expect_tx(bar_v + b, Cfg::V_BYTES);
+        ptx::tma_load_2d(smem + Cfg::OFF_V + b * Cfg::V_BYTES, &tm_kv, bar_v + b, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0);
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 64, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + Cfg::OFF_Q), k_addr = ptx::smem_u32(smem + Cfg::OFF_K);
       const uint32_t v_addr = ptx::smem_u32(smem + Cfg::OFF_V), p_addr = ptx::smem_u32(smem + Cfg::OFF_P);
       unsigned long long wq = 0, wk = 0, wp = 0, wv = 0;
       const long long t_start = clock64();
-      mbar_wait_prof(bar_q, 0, do_prof, wq);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait_prof(bar_k, ph, do_prof, wk);
+      auto issue_s = [&](int j) {
+        const int b = j & 1;
+        mbar_wait_prof(bar_k + b, (j >> 1) & 1, do_prof, wk);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16(tmem_s, ptx::umma_desc_sw128(q_addr + k * 32), ptx::umma_desc_sw128(k_addr + k * 32), idesc_s, k > 0);
-        ptx::umma_commit(bar_s);
-        mbar_wait_prof(bar_p, ph, do_prof, wp);  // P_j in smem, S_j and PV_{j-1} drained from TMEM
-        mbar_wait_prof(bar_v, ph, do_prof, wv);
+          ptx::umma_bf16(tmem_base + b * 64, ptx::umma_desc_sw128(q_addr + k * 32),
+                         ptx::umma_desc_sw128(k_addr + b * Cfg::K_BYTES + k * 32), idesc_s, k > 0);
+        ptx::umma_commit(bar_s + b);
+      };
+      mbar_wait_prof(bar_q, 0, do_prof, wq);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int b = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait_prof(bar_p + b, ph, do_prof, wp);  // P_j in smem; S_j and PV_{j-1} drained from TMEM
+        mbar_wait_prof(bar_v + b, ph, do_prof, wv);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + (k >> 2) * (Cfg::QT * 128) + (k & 3) * 32),
-                         ptx::umma_desc_sw128(v_addr + k * 2048), idesc_pv, k > 0);
-        ptx::umma_commit(bar_pv);
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + b * Cfg::P_BYTES + k * 32),
+                         ptx::umma_desc_sw128(v_addr + b * Cfg::V_BYTES + k * 2048), idesc_pv, k > 0);
+        ptx::umma_commit(bar_pv + b);
+        if (j + 2 < n_tiles) issue_s(j + 2);
       }
       if (do_prof) {
         prof[0] = (unsigned long long)(clock64() - t_start), prof[1] = wq, prof[2] = wk, prof[3] = wp, prof[4] = wv;
@@ -198,87 +259,84 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int inner, const UttT
       }
     }
   } else {
-    // ---------------- softmax / correction / epilogue: two threads per query row.
-    // Thread (row r, half hc) owns key columns [64 hc, 64 hc + 64) of S and output columns [32 hc, 32 hc + 32) of O.
-    const int quarter = warp & 3;        // TMEM lane quarter this warp may touch
-    const int hc = (warp - 2) >> 2;
+    // ---------------- softmax / correction / epilogue: one query row per thread
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float pad_bias = u.pad_key_bias * 1.4426950408889634f;
-    float o[32];
+    f32x2 o2[32];  // 64 output columns as packed fp32 pairs
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    for (int d = 0; d < 32; ++d) o2[d] = pack2(0.f, 0.f);
     float mrun = -INFINITY, lrun = 0.f;
     const bool sp = do_prof && warp == 2;
     unsigned long long ws = 0, wbar = 0, wpv = 0;
     const long long ts_start = clock64();
-    uint8_t* p_row = smem + Cfg::OFF_P + hc * (Cfg::QT * 128) + r * 128;  // K-block hc of the P tile, row r
-    for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t ph = j & 1;
-      const int k0 = j * Cfg::KT + hc * 64;
-      const bool ragged = (k0 + 64 > L);  // this half holds the pad token and/or rows past this utterance
-      mbar_wait_prof(bar_s, ph, sp, ws);
+    auto add_pv = [&](int jprev) {  // O += PV_{jprev}
+      mbar_wait_prof(bar_pv + (jprev & 1), (jprev >> 1) & 1, sp, wpv);
       ptx::tc_fence_after();
-      // The masking of ragged tiles (pad token, keys past the utterance) is hoisted out of the element loops: full tiles
-      // run a branch-free path.  Max and sum use 4 independent accumulators to break the dependency chains.
-      float mt;
-      if (!ragged) mt = attn_rowmax<false>(tmem_s + lane_off + hc * 64, k0, L, 0.f);
-      else mt = attn_rowmax<true>(tmem_s + lane_off + hc * 64, k0, L, pad_bias / scale_log2);
-      red[hc * Cfg::QT + r] = mt;
-      {
-        const long long tb = sp ? clock64() : 0;
-        named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
-        if (sp) wbar += (unsigned long long)(clock64() - tb);
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t a[16], b2[16];
+        ptx::tmem_ld16(tmem_pv + lane_off + c, a);
+        ptx::tmem_ld16(tmem_pv + lane_off + c + 16, b2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o2[c / 2 + i] = add2(o2[c / 2 + i], pack2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])));
+          o2[c / 2 + 8 + i] = add2(o2[c / 2 + 8 + i], pack2(__uint_as_float(b2[2 * i]), __uint_as_float(b2[2 * i + 1])));
+        }
       }
-      mt = fmaxf(mt, red[(hc ^ 1) * Cfg::QT + r]);
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      const int k0 = j * Cfg::KT;
+      const bool ragged = (k0 + Cfg::KT > L);  // tile holds the pad token and/or rows past this utterance
+      uint8_t* p_row = smem + Cfg::OFF_P + b * Cfg::P_BYTES + r * 128;
+      mbar_wait_prof(bar_s + b, (j >> 1) & 1, sp, ws);
+      ptx::tc_fence_after();
+      const uint32_t ts = tmem_base + b * 64 + lane_off;
+      float mt;
+      if (!ragged) mt = attn_rowmax<false>(ts, k0, L, 0.f);
+      else mt = attn_rowmax<true>(ts, k0, L, pad_bias / scale_log2);
       const float mnew = fmaxf(mrun, mt * scale_log2);  // finite: key 0 of the first tile is always valid
       const float corr = ex2_approx(mrun - mnew);
       float psum;
-      if (!ragged) psum = attn_exp_store<false>(tmem_s + lane_off + hc * 64, p_row, r, k0, L, scale_log2, mnew, 0.f);
-      else psum = attn_exp_store<true>(tmem_s + lane_off + hc * 64, p_row, r, k0, L, scale_log2, mnew, pad_bias);
+      if (!ragged) psum = attn_exp_store<false>(ts, p_row, r, k0, L, scale_log2, mnew, 0.f);
+      else psum = attn_exp_store<true>(ts, p_row, r, k0, L, scale_log2, mnew, pad_bias);
+      if (j > 0) add_pv(j - 1);  // issued an iteration ago: complete by now; frees the PV accumulator for PV_j
       lrun = lrun * corr + psum;
       mrun = mnew;
+      if (__any_sync(0xffffffffu, corr != 1.f)) {  // once the running max has settled no row of the warp needs a rescale
+        const f32x2 c2 = pack2(corr, corr);
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] *= corr;
+        for (int d = 0; d < 32; ++d) o2[d] = mul2(o2[d], c2);
+      }
       ptx::tc_fence_before();
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      ptx::mbar_arrive(bar_p);
-      mbar_wait_prof(bar_pv, ph, sp, wpv);
-      ptx::tc_fence_after();
-      {
-        uint32_t a[16], b[16];
-        ptx::tmem_ld16(tmem_pv + lane_off + hc * 32, a);
-        ptx::tmem_ld16(tmem_pv + lane_off + hc * 32 + 16, b);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          o[i] += __uint_as_float(a[i]);
-          o[16 + i] += __uint_as_float(b[i]);
-        }
-      }
+      ptx::mbar_arrive(bar_p + b);
     }
+    add_pv(n_tiles - 1);
     if (sp && lane == 0) prof[8] = (unsigned long long)(clock64() - ts_start), prof[9] = ws, prof[10] = wbar, prof[11] = wpv;
     ptx::tc_fence_before();
-    // total row sum = both halves
-    red[hc * Cfg::QT + r] = lrun;
-    named_bar_sync(1, 32 * Cfg::N_SOFTMAX_WARPS);
-    lrun += red[(hc ^ 1) * Cfg::QT + r];
     const int qi = q0 + r;
     if (qi < nk) {
       const float inv = 1.f / lrun;
-      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D + hc * 32;
+      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
 #pragma unroll
-      for (int d = 0; d < 32; d += 8) {
+      for (int d = 0; d < 32; d += 4) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) unpack2(o2[d + i], x[2 * i], x[2 * i + 1]);
         uint4 pk;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[d + 0] * inv, o[d + 1] * inv);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[d + 4] * inv, o[d + 5] * inv);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(o[d + 6] * inv, o[d + 7] * inv);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0] * inv, x[1] * inv);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(x[2] * inv, x[3] * inv);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(x[4] * inv, x[5] * inv);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(x[6] * inv, x[7] * inv);
         pk.x = *reinterpret_cast<uint32_t*>(&h0);
         pk.y = *reinterpret_cast<uint32_t*>(&h1);
         pk.z = *reinterpret_cast<uint32_t*>(&h2);
         pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(dst + d) = pk;
+        *reinterpret_cast<uint4*>(dst + 2 * d) = pk;
       }
     }
   }
@@ -303,17 +361,19 @@ template <typename Enc>
 inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, int M, const UttTable* utt, const int4* work,
                           int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err,
                           unsigned long long* prof = nullptr, bool pdl = false) {
-  CUtensorMap tm;
+  CUtensorMap tm_q, tm_kv;
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    *err = "cuTensorMapEncodeTiled failed for the attention QKV map";
-    return -2;
+  for (int i = 0; i < 2; ++i) {
+    cuuint32_t box[2] = {64, (cuuint32_t)(i == 0 ? AttnTcCfg::QT : AttnTcCfg::KT)};
+    CUresult r = encode(i == 0 ? &tm_q : &tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      *err = "cuTensorMapEncodeTiled failed for the attention QKV map";
+      return -2;
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -322,7 +382,7 @@ inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel, tm, inner, utt, work, static_cast<bf16*>(out), ldo,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel, tm_q, tm_kv, inner, utt, work, static_cast<bf16*>(out), ldo,
                                      scale * 1.4426950408889634f, prof);
   if (e != cudaSuccess) {
     *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);

@@ -500,17 +500,21 @@ Res res_of(Plan* pl, int r) {
 int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
                  float* out_f32, void* out_act, long long ld_act, cudaStream_t s) {
   if (h->stopped()) return 0;
-  h->launch_counter++;
+  h->launch_counter += 2;
   const int C = h->C();
   const double* stats = pl->stats + (long long)site * pl->B * 16;
-  const int blocks = (R.M + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK;
+  float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
+  CKR(launch_ex(h, gn_finalize_kernel, dim3((pl->B * 8 + 127) / 128), dim3(128), 0, s, 1, stats, (const double*)gn.bias_gsum,
+                (const UttTable*)R.utt, pl->B, C / 8, mr));
+  const long long items = (long long)R.M * (C / 8);
+  const int blocks = (int)((items + 255) / 256);
   if (h->bf)
     return launch_ex(h, gn_apply_kernel<bf16, false>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                     (const int*)R.info, (const UttTable*)R.utt, stats, (const double*)gn.bias_gsum, (const float*)gn.gamma,
-                     (const float*)gn.beta, addvec, resid, (long long)C, out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
+                     (const int*)R.info, (const float2*)mr, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                     out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
   return launch_ex(h, gn_apply_kernel<float, true>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                   (const int*)R.info, (const UttTable*)R.utt, stats, (const double*)gn.bias_gsum, (const float*)gn.gamma,
-                   (const float*)gn.beta, addvec, resid, (long long)C, out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
+                   (const int*)R.info, (const float2*)mr, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                   out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
 }
 
 // Conv k=3 (+bias) -> fp32 raw output + GroupNorm statistics for site `site`.

@@ -570,7 +570,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                                               int acc, uint32_t gn_slots, uint32_t gn_counters) {
   const int half = ewarp >> 2;
   const int q = ewarp & 3;
-  const int info = load_row_info(p, m0 + lane);
+  // STORE / SNAKE never look at the row flags: skip the (L2-latency) load that would sit on the tile's critical path
+  const int info = (MODE == EPI_STORE || MODE == EPI_SNAKE) ? ROW_VALID : load_row_info(p, m0 + lane);
   const uint32_t valid_mask = __ballot_sync(0xffffffffu, (info & ROW_VALID) != 0);
   const uint32_t instat_mask = __ballot_sync(0xffffffffu, (info & ROW_INSTAT) != 0);
   bool do_stats = false, uniform = false;

@@ -125,103 +125,86 @@ __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M
   atomicAdd(stats + ((long long)utt * 8 + g) * 2 + 1, (double)ss);
 }
 
-// y = valid ? Mish(GN(h)) + addvec[c] : 0;  y += resid[m, c];  -> out_f32 and/or out_act.   8 channels per thread.
-// GroupNorm statistics -> (mean, rstd) per (utterance, group) are derived per block, in double, from the fp64 sums:
+// GroupNorm statistics -> (mean, rstd) per (utterance, group), in double from the fp64 sums.
 // sums = epilogue sums + bias_rows * (sum_c b_c, sum_c b_c^2) for the padded frames that are never materialised
 // (DESIGN.md "pad-aware packing"), over group_ch * t_res elements (reference decoder.py:35-45 normalises over the
-// PADDED length).  A block covers ROWS_PER_BLOCK consecutive rows, i.e. at most a handful of utterances.
-constexpr int GN_ROWS_PER_BLOCK = 16;
-constexpr int GN_MAX_UTT_PER_BLOCK = 8;
+// PADDED length).
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const double* __restrict__ bias_gsum,
+                                   const UttTable* __restrict__ utt, int n_utt, int group_ch, float2* __restrict__ mr) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_utt * 8) return;
+  const int b = i >> 3, g = i & 7;
+  const UttTable u = utt[b];
+  const double n = (double)group_ch * (double)u.t_res;
+  const double s = stats[(long long)i * 2] + (double)u.bias_rows * bias_gsum[g * 2];
+  const double ss = stats[(long long)i * 2 + 1] + (double)u.bias_rows * bias_gsum[g * 2 + 1];
+  const double mean = s / n;
+  const double var = fmax(ss / n - mean * mean, 0.0);
+  mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+}
+
+// y = valid ? Mish(GN(h)) + addvec[c] : 0;  y += resid[m, c];  -> out_f32 and/or out_act.   8 channels per thread.
 template <typename T, bool PRECISE>
 __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int M, int C, int group_ch,
-                                const int* __restrict__ row_info, const UttTable* __restrict__ utt,
-                                const double* __restrict__ stats, const double* __restrict__ bias_gsum,
+                                const int* __restrict__ row_info, const float2* __restrict__ mr,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ addvec, const float* __restrict__ resid, long long ld_resid,
                                 float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act, long long ld_act) {
-  __shared__ float2 mr_s[GN_MAX_UTT_PER_BLOCK * 8];
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  const int m_first = blockIdx.x * GN_ROWS_PER_BLOCK;
-  const int m_last = min(m_first + GN_ROWS_PER_BLOCK, M) - 1;
-  const int u_first = __ldg(row_info + m_first) & ROW_UTT_MASK;
-  const int u_last = __ldg(row_info + m_last) & ROW_UTT_MASK;
-  if (threadIdx.x < GN_MAX_UTT_PER_BLOCK * 8) {
-    const int b = u_first + (threadIdx.x >> 3), g = threadIdx.x & 7;
-    if (b <= u_last) {
-      const UttTable u = utt[b];
-      const double n = (double)group_ch * (double)u.t_res;
-      const double s = stats[((long long)b * 8 + g) * 2] + (double)u.bias_rows * bias_gsum[g * 2];
-      const double ss = stats[((long long)b * 8 + g) * 2 + 1] + (double)u.bias_rows * bias_gsum[g * 2 + 1];
-      const double mean = s / n;
-      const double var = fmax(ss / n - mean * mean, 0.0);
-      mr_s[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = C >> 3;
+  const int m = (int)(idx / c8);
+  if (m >= M) return;
+  const int c = (int)(idx % c8) * 8;
+  const int info = __ldg(row_info + m);
+  const bool valid = (info & ROW_VALID) != 0;
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = 0.f;
+  if (valid) {
+    const int b = info & ROW_UTT_MASK;
+    const float2 st = __ldg(mr + (long long)b * 8 + c / group_ch);  // group_ch % 8 == 0: one group per thread
+    const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
+    const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float x[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf((x[i] - st.x) * st.y, ga[i], be[i]);
+      y[i] = PRECISE ? mish_precise(z) : mish_f(z);
+    }
+    if (addvec) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addvec + c)), a1 = __ldg(reinterpret_cast<const float4*>(addvec + c + 4));
+      y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w, y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
     }
   }
-  __syncthreads();
-  const int c8 = C >> 3;
-  for (int idx = threadIdx.x; idx < GN_ROWS_PER_BLOCK * c8; idx += blockDim.x) {
-    const int m = m_first + idx / c8;
-    if (m >= M) break;
-    const int c = (idx % c8) * 8;
-    const int info = __ldg(row_info + m);
-    const bool valid = (info & ROW_VALID) != 0;
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = 0.f;
-    if (valid) {
-      const int ul = (info & ROW_UTT_MASK) - u_first;
-      float2 st;
-      if (ul < GN_MAX_UTT_PER_BLOCK) {
-        st = mr_s[ul * 8 + c / group_ch];  // group_ch % 8 == 0: one group per thread
-      } else {  // more than 8 utterances inside 16 rows (1-frame utterances): derive directly
-        const int b = info & ROW_UTT_MASK, g = c / group_ch;
-        const UttTable u = utt[b];
-        const double n = (double)group_ch * (double)u.t_res;
-        const double s = stats[((long long)b * 8 + g) * 2] + (double)u.bias_rows * bias_gsum[g * 2];
-        const double ss = stats[((long long)b * 8 + g) * 2 + 1] + (double)u.bias_rows * bias_gsum[g * 2 + 1];
-        const double mean = s / n;
-        st = make_float2((float)mean, (float)(1.0 / sqrt(fmax(ss / n - mean * mean, 0.0) + 1e-5)));
-      }
-      const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
-      const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-      const float x[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-      const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = fmaf((x[i] - st.x) * st.y, ga[i], be[i]);
-        y[i] = PRECISE ? mish_precise(z) : mish_f(z);
-      }
-      if (addvec) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(addvec + c)), a1 = __ldg(reinterpret_cast<const float4*>(addvec + c + 4));
-        y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w, y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
-      }
-    }
-    if (resid) {
-      const float4 r0 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
-      const float4 r1 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c + 4);
-      y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w, y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
-    }
-    if (out_f32) {
-      *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
-    }
-    if (out_act) {
-      T* d = out_act + (long long)m * ld_act + c;
-      if constexpr (sizeof(T) == 2) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]), p3 = __floats2bfloat162_rn(y[6], y[7]);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&p0), o.y = *reinterpret_cast<uint32_t*>(&p1);
-        o.z = *reinterpret_cast<uint32_t*>(&p2), o.w = *reinterpret_cast<uint32_t*>(&p3);
-        *reinterpret_cast<uint4*>(d) = o;
-      } else {
-        *reinterpret_cast<float4*>(d) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(d + 4) = make_float4(y[4], y[5], y[6], y[7]);
-      }
+  if (resid) {
+    const float4 r0 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
+    const float4 r1 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c + 4);
+    y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w, y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
+  }
+  if (out_f32) {
+    *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+  if (out_act) {
+    T* d = out_act + (long long)m * ld_act + c;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]), p3 = __floats2bfloat162_rn(y[6], y[7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&p0), o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2), o.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(d) = o;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(y[4], y[5], y[6], y[7]);
     }
   }
 }
