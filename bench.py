@@ -68,10 +68,14 @@ class ClockSampler:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
+    def mark(self):
+        """Index of the next sample: call at the start and end of the timed region."""
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.rows:
+        for line in self.rows[lo:hi]:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -210,14 +214,20 @@ def main():
 
     dev_step = lambda: model.solve(z, ts, mu, mask, lengths=lengths, spks=spks)
     host_step = (lambda: model.solve_host(z_h, ts.cpu(), mu_h, lengths, device=dev)) if not args.spks else dev_step
-    t_w = time.perf_counter()
-    n_w = 0
-    while n_w < args.warmup or time.perf_counter() - t_w < 1.5:  # >= W steps and >= 1.5 s: clocks and caches settled
-        out = dev_step()
-        torch.cuda.synchronize(dev)
-        n_w += 1
+    # The sampler (an nvidia-smi child) starts BEFORE the warm-up so that its start-up never lands in the timed region;
+    # only the samples taken between the two marks are reported.
     with ClockSampler(local_rank) as clk:
+        t_w = time.perf_counter()
+        n_w = 0
+        while n_w < args.warmup or time.perf_counter() - t_w < 1.5:  # >= W steps and >= 1.5 s: clocks and caches settled
+            out = dev_step()
+            torch.cuda.synchronize(dev)
+            n_w += 1
+        lo = clk.mark()
         ms_total, _, out = timed(dev_step, args.steps)
+        time.sleep(0.12)
+        hi = clk.mark()
+    clocks = clk.summary(lo, max(hi, lo + 1))
     for _ in range(3):
         host_step()
     _, wall_ms_e2e, out_h = timed(host_step, args.steps)
@@ -232,6 +242,10 @@ def main():
     flops = P.synthetic.algorithmic_flops(lengths, 384, args.ode_steps) + 8.0 * args.spks * 384 * sum(lengths) * args.ode_steps
     achieved = flops / (ms_step * 1e-3) / 1e12
     n_bytes = mu_h.numel() * 4
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
+    if args.workload == "cfg2" and args.precision == "bf16" and args.ode_steps == N_STEPS_ODE and not args.spks and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_decode")  # ncu dram__bytes_{read,write}.sum over every launch of one decode
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -245,10 +259,10 @@ def main():
                 "h2d_bytes_per_step": 2 * n_bytes, "d2h_bytes_per_step": n_bytes, "api": "cfm_solve_host (C ABI, pinned host buffers)" if not args.spks else "device-resident (no host-buffer entry with spks)"},
         "gpu_launches": int(info["kernels_per_solve"]) * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                     "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + ", sustained bf16",
                      "kernel": "whole decode = one graph launch (gemm_tc_kernel + attn_tc_kernel carry >97% of the FLOPs)",
                      "algorithmic_flops_per_launch": flops},
-        "clocks": clk.summary(),
+        "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
