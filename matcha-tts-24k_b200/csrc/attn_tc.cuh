@@ -98,7 +98,7 @@ __device__ __forceinline__ float attn_rowmax(uint32_t taddr, int k0, int L, floa
 // P = exp2(s * scale_log2 - m) for this thread's 64 columns -> bf16 -> smem in the UMMA K-major 128B-swizzled layout
 // (16-byte chunk c of row r lives at chunk c ^ (r & 7)); returns the row's partial sum.
 template <bool RAGGED>
-__device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, int r, int k0, int L, float scale_log2,
+__device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint32_t p_row, int r, int k0, int L, float scale_log2,
                                                 float mnew, float pad_bias_log2) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   f32x2 acc01 = pack2(0.f, 0.f), acc23 = pack2(0.f, 0.f);
@@ -143,7 +143,7 @@ __device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint8_t* p_row, 
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
       pk.z = *reinterpret_cast<uint32_t*>(&h2);
       pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = pk;
+      ptx::sts128_u32(p_row + ((chunk ^ (r & 7)) << 4), pk.x, pk.y, pk.z, pk.w);
     }
   }
   if constexpr (!RAGGED) {
@@ -291,7 +291,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const int b = j & 1;
       const int k0 = j * Cfg::KT;
       const bool ragged = (k0 + Cfg::KT > L);  // tile holds the pad token and/or rows past this utterance
-      uint8_t* p_row = smem + Cfg::OFF_P + b * Cfg::P_BYTES + r * 128;
+      const uint32_t p_row = ptx::smem_u32(smem + Cfg::OFF_P + b * Cfg::P_BYTES + r * 128);
       mbar_wait_prof(bar_s + b, (j >> 1) & 1, sp, ws);
       ptx::tc_fence_after();
       const uint32_t ts = tmem_base + b * 64 + lane_off;

@@ -126,6 +126,9 @@ struct cfm_handle {
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
   cudaStream_t own_stream = nullptr;
+  // plan workspace arena: grown on demand, kept across cfm_plan calls (a server re-plans for every new batch shape)
+  char* ws_base = nullptr;
+  size_t ws_cap = 0, ws_off = 0;
   int C() const { return cfg.channels; }
   int inner() const { return cfg.n_heads * cfg.head_dim; }
 };
@@ -173,6 +176,37 @@ int dev_alloc_t(cfm_handle* h, std::vector<void*>& arena, P** out, size_t count,
 void free_arena(std::vector<void*>& arena) {
   for (void* p : arena) cudaFree(p);
   arena.clear();
+}
+
+// Bump allocation from the handle's persistent workspace arena; falls back to cudaMalloc if the size estimate was short.
+int plan_alloc(cfm_handle* h, Plan* pl, void** out, size_t bytes) {
+  bytes = (bytes + 1023) / 1024 * 1024;
+  if (bytes == 0) bytes = 1024;
+  if (h->ws_off + bytes <= h->ws_cap) {
+    *out = h->ws_base + h->ws_off;
+    h->ws_off += bytes;
+    pl->bytes += bytes;
+    return 0;
+  }
+  return dev_alloc(h, pl->allocs, out, bytes, &pl->bytes);
+}
+template <typename P>
+int plan_alloc_t(cfm_handle* h, Plan* pl, P** out, size_t count) {
+  return plan_alloc(h, pl, reinterpret_cast<void**>(out), count * sizeof(P));
+}
+int ensure_workspace(cfm_handle* h, size_t need) {
+  if (need > h->ws_cap) {
+    if (h->ws_base) CK(cudaFree(h->ws_base));
+    h->ws_base = nullptr, h->ws_cap = 0;
+    const size_t cap = need + need / 8;
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->ws_base), cap));
+    h->ws_cap = cap;
+  }
+  // Guard rows and padding columns are never written by the kernels and must read as zero (stale bytes of a previous
+  // plan, reinterpreted as bf16, can be Inf/NaN and 0 * NaN poisons an MMA): clear what this plan will use (~0.1 ms/GB).
+  CK(cudaMemset(h->ws_base, 0, std::min(need, h->ws_cap)));
+  h->ws_off = 0;
+  return 0;
 }
 
 void free_plan(cfm_handle* h) {
@@ -907,6 +941,7 @@ void cfm_destroy(cfm_handle* h) {
   cudaDeviceSynchronize();
   free_plan(h);
   free_arena(h->wallocs);
+  if (h->ws_base) cudaFree(h->ws_base);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -1018,9 +1053,21 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     }
   }
   pl->n_work1 = (int)w1.size(), pl->n_work2 = (int)w2.size();
+  {  // size the persistent workspace arena for this plan (tables + state + activations + host-path staging)
+    const size_t C_ = h->C(), I_ = h->inner(), F_ = h->cfg.out_channels, es_ = h->es, M1_ = pl->M1, M2_ = pl->M2;
+    const size_t nt = pl->stages.size(), nres = 4 + h->cfg.n_mid_blocks;
+    size_t need = (size_t)batch * 2 * sizeof(UttTable) + (M1_ + M2_) * 4 + (w1.size() + w2.size()) * sizeof(int4);
+    need += nt * (4 + (size_t)h->cfg.in_channels * 4 + 2 * 4 * C_ * 4 + nres * C_ * 4);
+    need += 5 * M1_ * F_ * 4 + (2 * nres + 1) * (size_t)batch * (16 * 8 + 8 * 8);
+    need += M1_ * (size_t)roundup(h->cfg.in_channels, 64) * es_;
+    need += (M1_ + M2_) * (3 * C_ * 4 + (5 * C_ + 4 * I_ + 4 * C_) * es_);
+    need += 3 * (size_t)batch * F_ * t_pad * 4;
+    need += 64 * 1024 + (1 << 20);  // per-allocation 1 KB rounding, slack
+    CKR(ensure_workspace(h, need));
+  }
   auto up = [&](auto** dst, const auto& vec) -> int {
     using E = typename std::remove_reference<decltype(vec[0])>::type;
-    CKR(dev_alloc(h, pl->allocs, reinterpret_cast<void**>(dst), vec.size() * sizeof(E), &pl->bytes));
+    CKR(plan_alloc(h, pl, reinterpret_cast<void**>(dst), vec.size() * sizeof(E)));
     CK(cudaMemcpy(*dst, vec.data(), vec.size() * sizeof(E), cudaMemcpyHostToDevice));
     return 0;
   };
@@ -1037,33 +1084,33 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   std::vector<float> tv(n_t);
   for (int j = 0; j < n_t; ++j) tv[j] = pl->stages[j].t;
   CKR(up(&pl->tvals, tv));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->sinemb, (size_t)n_t * h->cfg.in_channels, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->temb_a, (size_t)n_t * T4, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->temb, (size_t)n_t * T4, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->tproj, (size_t)n_t * n_res * C, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->xstate, (size_t)pl->M1 * F, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->vout, (size_t)pl->M1 * F, &pl->bytes));
+  CKR(plan_alloc_t(h, pl, &pl->sinemb, (size_t)n_t * h->cfg.in_channels));
+  CKR(plan_alloc_t(h, pl, &pl->temb_a, (size_t)n_t * T4));
+  CKR(plan_alloc_t(h, pl, &pl->temb, (size_t)n_t * T4));
+  CKR(plan_alloc_t(h, pl, &pl->tproj, (size_t)n_t * n_res * C));
+  CKR(plan_alloc_t(h, pl, &pl->xstate, (size_t)pl->M1 * F));
+  CKR(plan_alloc_t(h, pl, &pl->vout, (size_t)pl->M1 * F));
   int n_k = 0;
   for (auto& st : pl->stages) n_k = std::max(n_k, st.kout + 1);
-  for (int j = 0; j < n_k; ++j) CKR(dev_alloc_t(h, pl->allocs, &pl->kbuf[j], (size_t)pl->M1 * F, &pl->bytes));
+  for (int j = 0; j < n_k; ++j) CKR(plan_alloc_t(h, pl, &pl->kbuf[j], (size_t)pl->M1 * F));
   const int n_sites = 2 * n_res + 1;
   pl->stats_bytes = (size_t)n_sites * batch * 16 * sizeof(double);
-  CKR(dev_alloc(h, pl->allocs, reinterpret_cast<void**>(&pl->stats), pl->stats_bytes, &pl->bytes));
-  CKR(dev_alloc_t(h, pl->allocs, &pl->gn_mr, (size_t)n_sites * batch * 8, &pl->bytes));
+  CKR(plan_alloc(h, pl, reinterpret_cast<void**>(&pl->stats), pl->stats_bytes));
+  CKR(plan_alloc_t(h, pl, &pl->gn_mr, (size_t)n_sites * batch * 8));
   pl->xin_ld = roundup(h->cfg.in_channels, 64);
-  CKR(dev_alloc(h, pl->allocs, &pl->xin, (size_t)pl->M1 * pl->xin_ld * es, &pl->bytes));
+  CKR(plan_alloc(h, pl, &pl->xin, (size_t)pl->M1 * pl->xin_ld * es));
   for (int r = 0; r < 2; ++r) {
     const size_t M = r == 0 ? pl->M1 : pl->M2;
-    CKR(dev_alloc_t(h, pl->allocs, &pl->hraw[r], M * C, &pl->bytes));
-    CKR(dev_alloc_t(h, pl->allocs, &pl->rres[r], M * C, &pl->bytes));
-    CKR(dev_alloc_t(h, pl->allocs, &pl->X[r], M * C, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->hact[r], M * C * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->Xn[r], M * C * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->qkv[r], M * 3 * I * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->ao[r], M * I * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->ffh[r], M * 4 * C * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->sin_[r], M * C * es, &pl->bytes));
-    CKR(dev_alloc(h, pl->allocs, &pl->cat[r], M * 2 * C * es, &pl->bytes));
+    CKR(plan_alloc_t(h, pl, &pl->hraw[r], M * C));
+    CKR(plan_alloc_t(h, pl, &pl->rres[r], M * C));
+    CKR(plan_alloc_t(h, pl, &pl->X[r], M * C));
+    CKR(plan_alloc(h, pl, &pl->hact[r], M * C * es));
+    CKR(plan_alloc(h, pl, &pl->Xn[r], M * C * es));
+    CKR(plan_alloc(h, pl, &pl->qkv[r], M * 3 * I * es));
+    CKR(plan_alloc(h, pl, &pl->ao[r], M * I * es));
+    CKR(plan_alloc(h, pl, &pl->ffh[r], M * 4 * C * es));
+    CKR(plan_alloc(h, pl, &pl->sin_[r], M * C * es));
+    CKR(plan_alloc(h, pl, &pl->cat[r], M * 2 * C * es));
   }
   CK(cudaDeviceSynchronize());
 
@@ -1106,9 +1153,9 @@ int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) {
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)pl->B * h->cfg.out_channels * pl->T;
   if (!pl->stage_mu) {  // device staging buffers live with the plan: no allocation on the per-call path
-    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_mu, n, &pl->bytes));
-    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_z, n, &pl->bytes));
-    CKR(dev_alloc_t(h, pl->allocs, &pl->stage_out, n, &pl->bytes));
+    CKR(plan_alloc_t(h, pl, &pl->stage_mu, n));
+    CKR(plan_alloc_t(h, pl, &pl->stage_z, n));
+    CKR(plan_alloc_t(h, pl, &pl->stage_out, n));
   }
   CK(cudaMemcpyAsync(pl->stage_mu, mu, n * 4, cudaMemcpyHostToDevice, h->own_stream));
   CK(cudaMemcpyAsync(pl->stage_z, z, n * 4, cudaMemcpyHostToDevice, h->own_stream));

@@ -393,6 +393,27 @@ def c_attnprof():
           f"softmax warp: total={p[8]} wait_s={p[9]} wait_rowmax_barrier={p[10]} wait_pv={p[11]}")
 
 
+def c_plantime():
+    """Host-side cost of cfm_load_weights and cfm_plan (row tables, workspace, graph capture) for cfg1 and cfg2."""
+    import time as _t
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16").eval().cuda()
+    P.synthetic.fill_named_seed(m.estimator, 1234)
+    t0 = _t.perf_counter(); m.refresh(torch.device("cuda", 0)); torch.cuda.synchronize(); t1 = _t.perf_counter()
+    print(f"[plantime] cfm_load_weights (pack 37 M params): {(t1 - t0) * 1e3:.1f} ms")
+    for name in ("cfg1", "cfg2", "cfg3"):
+        lengths = P.synthetic.config_lengths(name)
+        mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+        ts = torch.linspace(0, 1, 11, device="cuda")
+        torch.cuda.synchronize(); t0 = _t.perf_counter()
+        out = m.solve(z, ts, mu, mask, lengths=lengths); torch.cuda.synchronize(); t1 = _t.perf_counter()
+        out = m.solve(z, ts, mu, mask, lengths=lengths); torch.cuda.synchronize(); t2 = _t.perf_counter()
+        print(f"[plantime] {name}: first call (plan + capture + decode) {(t1 - t0) * 1e3:.1f} ms, second call {(t2 - t1) * 1e3:.1f} ms, {m.plan_info()}")
+
+
 CHECKS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("c_")}
 
 if __name__ == "__main__":
