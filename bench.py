@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ode-steps", type=int, default=N_STEPS_ODE, help="Euler steps per decode (BASELINE config 5 sweeps 2/4/10/32)")
+    ap.add_argument("--solver", default="euler", choices=["euler", "midpoint", "heun3", "rk4"],
+                    help="fixed-grid solver (the reference ships midpoint with 4 steps: matcha/inference.py:39-40)")
     ap.add_argument("--spks", type=int, default=0, help="speaker-vector width S for upstream-style conditioning (config 5: 96)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +182,7 @@ def main():
     else:  # every rank decodes its own copy of the workload
         T = 2 * ((max(all_lengths) + 1) // 2)
         lengths, scaling, job_frames = all_lengths, "weak", sum(all_lengths) * world
-    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    cp = types.SimpleNamespace(solver=args.solver, sigma_min=1e-4, use_mu_prior=True)
     model = P.CFM(200 + args.spks, 100, cp, P.synthetic.PROD, precision=args.precision, flags=args.flags).eval()
     P.synthetic.fill_named_seed(model.estimator, 1234)
     model = model.to(dev)
@@ -239,19 +241,21 @@ def main():
     value = job_frames / (ms_step * 1e-3)
     e2e_ms = wall_ms_e2e / args.steps
     pk = peaks()
-    flops = P.synthetic.algorithmic_flops(lengths, 384, args.ode_steps) + 8.0 * args.spks * 384 * sum(lengths) * args.ode_steps
+    nfe = args.ode_steps * {"euler": 1, "midpoint": 2, "heun3": 3, "rk4": 4}[args.solver]
+    flops = P.synthetic.algorithmic_flops(lengths, 384, nfe) + 8.0 * args.spks * 384 * sum(lengths) * nfe
     achieved = flops / (ms_step * 1e-3) / 1e12
     n_bytes = mu_h.numel() * 4
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
-    if args.workload == "cfg2" and args.precision == "bf16" and args.ode_steps == N_STEPS_ODE and not args.spks and os.path.exists(tpath):
+    if (args.workload == "cfg2" and args.precision == "bf16" and args.ode_steps == N_STEPS_ODE and args.solver == "euler"
+            and not args.spks and os.path.exists(tpath)):
         traffic = json.load(open(tpath)).get("dram_bytes_per_decode")  # ncu dram__bytes_{read,write}.sum over every launch of one decode
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": desc, "estimator": "prod C=384 H=6 d=64 n_blocks=2 mid=2 (37.03 M params, random init + N(0,0.1) 1-D)",
-                   "ode": f"euler x{args.ode_steps}, one CUDA graph", "spks": args.spks, "batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "t_pad": T,
+                   "ode": f"{args.solver} x{args.ode_steps}, one CUDA graph", "spks": args.spks, "batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "t_pad": T,
                    "rows_full": info["rows_full"], "l2": f"workspace {info['workspace_bytes'] / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
                    "parallelism": "utterance-sharded replicas, no collective" if world > 1 else "single GPU"},
         "rtf": (ms_step * 1e-3) / (job_frames * FRAME_SECONDS),
