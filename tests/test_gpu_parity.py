@@ -125,6 +125,20 @@ def test_upstream_style_speaker_conditioning(precision):
         m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
 
 
+def test_default_config_c320_tile_sized_utterances():
+    """The repo-default estimator (C=320, H=5: reference configs/model/decoder/default.yaml) with utterances longer than a
+    128-row tile, so that the per-tile GroupNorm path (40-channel groups across 32-column blocks) and BN=160 tiles run."""
+    ora, m = pair(syn.DEFAULT, "euler", "bf16")
+    lengths = [300, 171]
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=8)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
+    check(out, ref, "bf16", "default C=320, L=300/171, euler/2")
+    _, m32 = pair(syn.DEFAULT, "euler", "fp32")
+    check(m32.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda()), ref, "fp32", "default C=320 fp32")
+
+
 def test_forward_seed42_path_and_caller_context():
     """reference flow_matching.py:25-58 via the call pattern of inference.py:233-238 (inference_mode + fp16 autocast)."""
     ora, m = pair(TINY64, "euler", "fp32")
