@@ -531,8 +531,26 @@ Res res_of(Plan* pl, int r) {
   return v;
 }
 
+template <typename T, bool PRECISE>
+int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const float2* mr, const float* resid, const NormW& ln, cudaStream_t s) {
+  const int C = h->C();
+  const int blocks = (R.M * 32 + 255) / 256;
+#define CFM_GN_LN(NCH)                                                                                                     \
+  return launch_ex(h, gn_apply_ln_kernel<T, PRECISE, NCH>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, \
+                   R.M, C / 8, (const int*)R.info, mr, (const float*)gn.gamma, (const float*)gn.beta, resid, (long long)C, R.X,   \
+                   (long long)C, (const float*)ln.gamma, (const float*)ln.beta, static_cast<T*>(R.Xn), (long long)C)
+  switch (C / 128) {
+    case 1: CFM_GN_LN(1);
+    case 2: CFM_GN_LN(2);
+    case 3: CFM_GN_LN(3);
+    default: CFM_GN_LN(4);
+  }
+#undef CFM_GN_LN
+}
+
+// `fuse_ln` != nullptr (block2 of a resnet followed by a transformer stack, C % 128 == 0): also emits LayerNorm(out) -> R.Xn.
 int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
-                 float* out_f32, void* out_act, long long ld_act, cudaStream_t s) {
+                 float* out_f32, void* out_act, long long ld_act, cudaStream_t s, const NormW* fuse_ln = nullptr) {
   if (h->stopped()) return 0;
   h->launch_counter += 2;
   const int C = h->C();
@@ -540,6 +558,10 @@ int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int sit
   float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
   CKR(launch_ex(h, gn_finalize_kernel, dim3((pl->B * 8 + 127) / 128), dim3(128), 0, s, 1, stats, (const double*)gn.bias_gsum,
                 (const UttTable*)R.utt, pl->B, C / 8, mr));
+  if (fuse_ln) {
+    if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, mr, resid, *fuse_ln, s);
+    return launch_gn_ln<float, true>(h, R, gn, mr, resid, *fuse_ln, s);
+  }
   const long long items = (long long)R.M * (C / 8);
   const int blocks = (int)((items + 255) / 256);
   if (h->bf)
@@ -613,7 +635,7 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
 
 // ResnetBlock1D (reference decoder.py:48-63) on masked input A (K columns) -> fp32 residual stream R.X.
 int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const void* A, long long lda, int& site,
-               const float* tproj, cudaStream_t s) {
+               const float* tproj, cudaStream_t s, const NormW* fuse_ln) {
   const int C = h->C();
   CKR(run_conv_stats(h, pl, R, A, lda, w.conv1, site, s));
   {  // res_conv (1x1) on the same masked input -> fp32
@@ -625,16 +647,16 @@ int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const vo
   CKR(run_gn_apply(h, pl, R, w.gn1, site, tproj, nullptr, nullptr, R.hact, C, s));
   site++;
   CKR(run_conv_stats(h, pl, R, R.hact, C, w.conv2, site, s));
-  CKR(run_gn_apply(h, pl, R, w.gn2, site, nullptr, R.rres, R.X, nullptr, 0, s));
+  CKR(run_gn_apply(h, pl, R, w.gn2, site, nullptr, R.rres, R.X, nullptr, 0, s, fuse_ln));
   site++;
   return 0;
 }
 
 // BasicTransformerBlock (reference transformer.py:230-303).  If copy_dst != nullptr the FF2 epilogue also writes the
 // masked activation-type copy of the block output there (skip connection / next conv input).
-int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s) {
+int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s, bool ln1_done) {
   const int C = h->C(), I = h->inner();
-  CKR(run_layernorm(h, R, w.ln1, s));
+  if (!ln1_done) CKR(run_layernorm(h, R, w.ln1, s));
   {
     GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.qkv, nullptr, nullptr);
     p.mode = EPI_STORE, p.out_act = R.qkv, p.ld_act = 3 * I;
@@ -663,10 +685,12 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
 
 int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void* A, long long lda, int& site,
               const float* tproj, void* copy_dst, long long copy_ld, cudaStream_t s) {
-  CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, s));
+  // the resnet's last GroupNorm-apply also produces LayerNorm1 of the first transformer block when the width allows
+  const bool fuse = h->C() % 128 == 0 && h->C() <= 512 && !w.blocks.empty() && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS);
+  CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, s, fuse ? &w.blocks[0].ln1 : nullptr));
   for (size_t j = 0; j < w.blocks.size(); ++j) {
     const bool last = j + 1 == w.blocks.size();
-    CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s));
+    CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s, fuse && j == 0));
   }
   return 0;
 }

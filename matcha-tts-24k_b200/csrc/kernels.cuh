@@ -209,6 +209,79 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   }
 }
 
+// Last GroupNorm of a ResnetBlock1D fused with the first LayerNorm of the transformer stack that follows it
+// (reference decoder.py:62 -> transformer.py:249): one warp per row, NCH*128 channels.
+//   x  = (valid ? Mish(GN(h)) : 0) + resid     -> fp32 residual stream
+//   xn = LayerNorm(x) * ln_gamma + ln_beta      -> activation type (next GEMM's A operand)
+// Saves one pass over the fp32 stream and one launch per stage.
+template <typename T, bool PRECISE, int NCH>
+__global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, int M, int group_ch,
+                                   const int* __restrict__ row_info, const float2* __restrict__ mr,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ resid, long long ld_resid, float* __restrict__ out_f32,
+                                   long long ld_f32, const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
+                                   T* __restrict__ out_ln, long long ld_ln) {
+  constexpr int C = NCH * 128;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  if (row >= M) return;
+  const int info = __ldg(row_info + row);
+  const bool valid = (info & ROW_VALID) != 0;
+  const int b = info & ROW_UTT_MASK;
+  float y[NCH][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * ld_resid + c);
+    y[i][0] = r.x, y[i][1] = r.y, y[i][2] = r.z, y[i][3] = r.w;
+    if (valid) {
+      const float2 st = __ldg(mr + (long long)b * 8 + c / group_ch);
+      const float4 hv = *reinterpret_cast<const float4*>(h + (long long)row * ld_h + c);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float x[4] = {hv.x, hv.y, hv.z, hv.w}, ga[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf((x[j] - st.x) * st.y, ga[j], bb[j]);
+        y[i][j] += PRECISE ? mish_precise(z) : mish_f(z);
+      }
+    }
+    *reinterpret_cast<float4*>(out_f32 + (long long)row * ld_f32 + c) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+    s += (y[i][0] + y[i][1]) + (y[i][2] + y[i][3]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = y[i][j] - mean;
+      ss = fmaf(d, d, ss);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma + c)), be = __ldg(reinterpret_cast<const float4*>(ln_beta + c));
+    const float o0 = fmaf((y[i][0] - mean) * rstd, g.x, be.x), o1 = fmaf((y[i][1] - mean) * rstd, g.y, be.y);
+    const float o2 = fmaf((y[i][2] - mean) * rstd, g.z, be.z), o3 = fmaf((y[i][3] - mean) * rstd, g.w, be.w);
+    T* d = out_ln + (long long)row * ld_ln + c;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0), u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(d) = u;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
 // per-GroupNorm-site sums of the conv bias per group: [8][2] doubles (sum b, sum b^2)
 __global__ void bias_group_sums_kernel(const float* __restrict__ bias, int C, int group_ch, double* __restrict__ out) {
   const int g = threadIdx.x;
