@@ -92,6 +92,18 @@ int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* 
  * Decoder.forward(x, mask, mu, t, spks)).  The pointer must stay valid until that call has been enqueued. */
 int cfm_set_speakers(cfm_handle* h, const float* spks);
 
+/* Utterances never interact inside the solve (GroupNorm and attention are per utterance; reference decoder.py:35-45,
+ * transformer.py:253-258), so the next cfm_plan cuts the batch into up to `lanes` contiguous utterance groups of equal
+ * estimated cost whose kernel chains are parallel branches of the CUDA graph (one lane's kernels fill the partial last
+ * wave of another's).  A lane is never cut below `min_rows` packed full-resolution rows (<= 0: keep the current value).
+ * Results do not depend on the lane count.  Default 1 lane (measured slower on cfg2-4) / 4096 rows (env CFM_B200_LANES, CFM_B200_LANE_MIN_ROWS). */
+int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
+
+/* Kernel-selection switches for A/B measurements (take effect at the next cfm_plan / debug GEMM): "tma_epi" 0/1 (TMA-store
+ * GEMM epilogue), "pair_mode" 0/1/2 (CTA-pair GEMM never / where it measures faster / always), "pdl" 0/1, "cluster" 1/2/4.
+ * Results stay within the precision mode's tolerance for every setting. */
+int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
+
 /* Same with HOST buffers (pinned or pageable): H2D of mu and z, solve, D2H of out, then synchronises.
  * This is the call a non-PyTorch host (cgo / JNI / N-API) binds. */
 int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out);

@@ -36,7 +36,7 @@ def lengths_from_mask(mask: torch.Tensor):
 
 class CFM(torch.nn.Module):
     def __init__(self, in_channels, out_channel, cfm_params, decoder_params, precision: Optional[str] = None,
-                 flags: int = 0):
+                 flags: int = 0, lanes: Optional[int] = None, lane_min_rows: int = 0):
         super().__init__()
         self.n_feats = in_channels  # sic: the reference passes in_channels as n_feats (flow_matching.py:112-115)
         self.solver = cfm_params.solver
@@ -46,6 +46,8 @@ class CFM(torch.nn.Module):
         if self.precision not in N.PREC:
             raise ValueError(f"precision must be one of {sorted(N.PREC)}, got {self.precision!r}")
         self.flags = int(flags) | int(os.environ.get("CFM_B200_FLAGS", "0"))
+        # graph branches per decode (cfm_set_lanes); None keeps the library default / CFM_B200_LANES
+        self.lanes, self.lane_min_rows = lanes, int(lane_min_rows)
         cfg = config_from_decoder_params(in_channels, out_channel, **dict(decoder_params))
         est = EstimatorWeights(cfg)
         est._owner = [self]
@@ -74,7 +76,23 @@ class CFM(torch.nn.Module):
         object.__setattr__(self, "_device", device)
         object.__setattr__(self, "_weights_sig", None)
         object.__setattr__(self, "_plan_key", None)
+        if self.lanes is not None:
+            N.check(lib, handle, lib.cfm_set_lanes(handle, int(self.lanes), self.lane_min_rows))
         return lib, handle
+
+    def set_option(self, key: str, value: int):
+        """cfm_set_option: kernel-selection switches for A/B measurements; drops the current plan."""
+        if self._handle is None:
+            raise RuntimeError("set_option needs a live handle: call refresh(device) or run a decode first")
+        N.check(self._lib, self._handle, self._lib.cfm_set_option(self._handle, key.encode(), int(value)))
+        object.__setattr__(self, "_plan_key", None)
+
+    def set_lanes(self, lanes: int, min_rows: int = 0):
+        """Number of independent utterance groups the next plan runs as parallel graph branches (results unchanged)."""
+        self.lanes, self.lane_min_rows = int(lanes), int(min_rows)
+        if self._handle is not None:
+            N.check(self._lib, self._handle, self._lib.cfm_set_lanes(self._handle, self.lanes, self.lane_min_rows))
+            object.__setattr__(self, "_plan_key", None)
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._lib is not None:

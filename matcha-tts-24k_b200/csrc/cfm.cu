@@ -72,8 +72,16 @@ struct OdeStage {
   bool write_state;
 };
 
+struct LaneDef {  // a contiguous group of utterances that runs as its own branch of the CUDA graph
+  int b0 = 0, nb = 0;      // utterance range
+  int r2 = 0, m2 = 0;      // first half-resolution row, half-resolution rows (full resolution: 2x both)
+  int w0[2] = {0, 0};      // first attention work item per resolution
+  int nw[2] = {0, 0};      // attention work items per resolution
+};
+
 struct Plan {
   int B = 0, T = 0;
+  std::vector<LaneDef> lanes;
   std::vector<int> L;
   int M1 = 0, M2 = 0;
   std::vector<OdeStage> stages;
@@ -120,12 +128,22 @@ struct cfm_handle {
   int pdl = 0;                                  // programmatic dependent launch between the kernels of a decode (CFM_B200_PDL=1);
                                                 // measured neutral on cfg1/cfg2, so off by default
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
+  int tma_epi = 1 << EPI_RESID;                 // bit m: TMA-store epilogue for EpiMode m.  Measured on cfg2: the in-place
+                                                // residual add through cp.reduce.async.bulk saves 1.2 ms per decode; STORE / SNAKE /
+                                                // MASK are 0-2 ms slower than the transposing epilogue, so they stay off
   long long launch_counter = 0;
   const float* spks = nullptr;  // device (B, S) speaker vectors for the next pack (cfm_set_speakers); S = in_channels - 2 F
   unsigned long long* attn_prof = nullptr;  // debug: device buffer for attn_tc_kernel's CTA-0 cycle counters
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
   cudaStream_t own_stream = nullptr;
+  // Utterances never interact inside the solve, so a batch is cut into `lanes_req` contiguous groups ("lanes") whose kernel
+  // chains are independent branches of the graph: one lane's kernels fill the partial last wave / launch gaps of another's.
+  int lanes_req = 1;  // measured on cfg2-cfg4: 2 lanes +2 %, 3 lanes +12 % decode time: off by default
+  int lane_min_rows = 4096;  // do not cut below this many full-resolution rows per lane
+  std::vector<cudaStream_t> lane_streams;
+  std::vector<cudaEvent_t> lane_events;
+  cudaEvent_t fork_event = nullptr;
   // plan workspace arena: grown on demand, kept across cfm_plan calls (a server re-plans for every new batch shape)
   char* ws_base = nullptr;
   size_t ws_cap = 0, ws_off = 0;
@@ -367,6 +385,20 @@ int make_tmap(cfm_handle* h, CUtensorMap* tm, const void* base, long long inner_
   return 0;
 }
 
+// Output tensor map of the TMA-store epilogue: 32 x 32 element boxes, bf16 (SWIZZLE_64B rows of 64 B) or fp32 (SWIZZLE_128B).
+int make_out_tmap(cfm_handle* h, CUtensorMap* tm, const void* base, bool f32, long long cols, long long rows, long long ld_elems) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, CFM_ERR_CUDA, "cuTensorMapEncodeTiled (output map) failed (%d) cols=%lld rows=%lld ld=%lld", (int)r, cols, rows, ld_elems);
+  return 0;
+}
+
 int pick_bn(int N) {
   if (N % 256 == 0) return 256;
   if (N % 192 == 0) return 192;
@@ -403,24 +435,24 @@ int launch_ex(cfm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 
 template <int BN>
-int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
-                 cudaStream_t s) {
+int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                 const GemmParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
   const int CL = p.cluster;
   const int m_super = ((p.M + 127) / 128 + CL - 1) / CL;
   const int super_tiles = m_super * ((p.N + BN - 1) / BN);
   const int clusters = std::min(super_tiles, h->max_clusters[CL]);
-  return launch_ex(h, gemm_tc_kernel<BN>, dim3(clusters * CL), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, CL, a0, a1, w, p);
+  return launch_ex(h, gemm_tc_kernel<BN>, dim3(clusters * CL), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, CL, a0, a1, w, o, p);
 }
 
 template <int BN>
-int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
-                  cudaStream_t s) {
+int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                  const GemmParams& p, cudaStream_t s) {
   using Cfg = Tc2Cfg<BN>;
   const int m_pairs = (p.M + 255) / 256;
   const int pair_tiles = m_pairs * ((p.N + BN - 1) / BN);
   const int pairs = std::min(pair_tiles, h->max_clusters[2]);
-  return launch_ex(h, gemm_tc2_kernel<BN>, dim3(pairs * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 2, a0, a1, w, p);
+  return launch_ex(h, gemm_tc2_kernel<BN>, dim3(pairs * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 2, a0, a1, w, o, p);
 }
 
 template <int BN>
@@ -470,24 +502,35 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     const int src = p.A[i] ? i : 0;
     CKR(make_tmap(h, &tmA[i], p.A[src], p.lda[src], p.a_rows[src], p.lda[src] * 2, 64, 128));
   }
+  // TMA-store epilogue (gemm.cuh epilogue_tile_tma): bf16-output modes, and the in-place fp32 residual add when no
+  // activation copy is wanted (L2 performs x += acc + bias through cp.reduce.async.bulk).
+  const bool bf_mode = p.mode == EPI_STORE || p.mode == EPI_SNAKE || p.mode == EPI_MASK;
+  const bool red_mode = p.mode == EPI_RESID && p.out_act == nullptr && p.resid != nullptr && p.resid == p.out_f32 && p.ld_resid == p.ld_f32;
+  p.tma_epi = (((h->tma_epi >> p.mode) & 1) && (bf_mode || red_mode) && p.N % 8 == 0 && bn % 32 == 0) ? 1 : 0;
+  CUtensorMap tmO = tmA[0];
+  if (p.tma_epi) {
+    if (red_mode) CKR(make_out_tmap(h, &tmO, p.out_f32, true, p.N, p.M, p.ld_f32));
+    else CKR(make_out_tmap(h, &tmO, p.out_act, false, p.N, p.M, p.ld_act));
+  }
   // CTA-pair kernel where it measures faster: long reductions (k=3 convs, FF2); short-K GEMMs are epilogue-bound there.
-  p.pair = (h->pair_mode == 2 || (h->pair_mode == 1 && p.n_taps * p.K >= 1024)) && bn >= 128 ? 1 : 0;
+  const bool pair_ok = h->pair_mode == 2 || (h->pair_mode == 1 && p.n_taps * p.K >= 1024);
+  p.pair = pair_ok && bn >= 128 ? 1 : 0;
   p.cluster = p.pair ? 1 : h->cluster;
   CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, p.pair ? bn / 2 : bn / p.cluster));
   if (p.pair) {
     switch (bn) {
-      case 128: return launch_tc2_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
-      case 160: return launch_tc2_bn<160>(h, tmA[0], tmA[1], tmW, p, s);
-      case 192: return launch_tc2_bn<192>(h, tmA[0], tmA[1], tmW, p, s);
-      default: return launch_tc2_bn<256>(h, tmA[0], tmA[1], tmW, p, s);
+      case 128: return launch_tc2_bn<128>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+      case 160: return launch_tc2_bn<160>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+      case 192: return launch_tc2_bn<192>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+      default: return launch_tc2_bn<256>(h, tmA[0], tmA[1], tmW, tmO, p, s);
     }
   }
   switch (bn) {
-    case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, p, s);
-    case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, p, s);
-    case 160: return launch_tc_bn<160>(h, tmA[0], tmA[1], tmW, p, s);
-    case 192: return launch_tc_bn<192>(h, tmA[0], tmA[1], tmW, p, s);
-    default: return launch_tc_bn<256>(h, tmA[0], tmA[1], tmW, p, s);
+    case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+    case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+    case 160: return launch_tc_bn<160>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+    case 192: return launch_tc_bn<192>(h, tmA[0], tmA[1], tmW, tmO, p, s);
+    default: return launch_tc_bn<256>(h, tmA[0], tmA[1], tmW, tmO, p, s);
   }
 }
 
@@ -509,25 +552,35 @@ GemmParams gemm_base(int M, const void* A, long long lda, int a_rows, const Gemm
   return p;
 }
 
-struct Res {  // per-resolution view of the plan
+struct Res {  // per-resolution view of one lane of the plan (all pointers already offset to the lane's first row)
   int M;
-  UttTable* utt;
+  int b0, nb;      // utterance range of the lane
+  UttTable* utt;   // whole-batch table (indexed by the global utterance id stored in row_info / work items)
   int* info;
   int4* work;
   int n_work;
   float *hraw, *rres, *X;
   void *hact, *Xn, *qkv, *ao, *ffh, *sin_, *cat;
+  void *qkv_all, *ao_all;  // un-offset buffers + total rows: the attention kernel addresses rows through UttTable.start
+  int M_all;
 };
-Res res_of(Plan* pl, int r) {
+Res res_of(cfm_handle* h, Plan* pl, int r, const LaneDef& ln) {
+  const long long C = h->C(), I = h->inner();
+  const int es = h->es;
+  const long long row0 = r == 0 ? 2LL * ln.r2 : ln.r2;
   Res v;
-  v.M = r == 0 ? pl->M1 : pl->M2;
+  v.M = r == 0 ? 2 * ln.m2 : ln.m2;
+  v.b0 = ln.b0, v.nb = ln.nb;
   v.utt = r == 0 ? pl->utt1 : pl->utt2;
-  v.info = r == 0 ? pl->info1 : pl->info2;
-  v.work = r == 0 ? pl->work1 : pl->work2;
-  v.n_work = r == 0 ? pl->n_work1 : pl->n_work2;
-  v.hraw = pl->hraw[r], v.rres = pl->rres[r], v.X = pl->X[r];
-  v.hact = pl->hact[r], v.Xn = pl->Xn[r], v.qkv = pl->qkv[r], v.ao = pl->ao[r], v.ffh = pl->ffh[r];
-  v.sin_ = pl->sin_[r], v.cat = pl->cat[r];
+  v.info = (r == 0 ? pl->info1 : pl->info2) + row0;
+  v.work = (r == 0 ? pl->work1 : pl->work2) + ln.w0[r];
+  v.n_work = ln.nw[r];
+  v.hraw = pl->hraw[r] + row0 * C, v.rres = pl->rres[r] + row0 * C, v.X = pl->X[r] + row0 * C;
+  v.hact = act_off(pl->hact[r], row0 * C, es), v.Xn = act_off(pl->Xn[r], row0 * C, es);
+  v.qkv = act_off(pl->qkv[r], row0 * 3 * I, es), v.ao = act_off(pl->ao[r], row0 * I, es);
+  v.ffh = act_off(pl->ffh[r], row0 * 4 * C, es);
+  v.qkv_all = pl->qkv[r], v.ao_all = pl->ao[r], v.M_all = r == 0 ? pl->M1 : pl->M2;
+  v.sin_ = act_off(pl->sin_[r], row0 * C, es), v.cat = act_off(pl->cat[r], row0 * 2 * C, es);
   return v;
 }
 
@@ -556,8 +609,8 @@ int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int sit
   const int C = h->C();
   const double* stats = pl->stats + (long long)site * pl->B * 16;
   float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
-  CKR(launch_ex(h, gn_finalize_kernel, dim3((pl->B * 8 + 127) / 128), dim3(128), 0, s, 1, stats, (const double*)gn.bias_gsum,
-                (const UttTable*)R.utt, pl->B, C / 8, mr));
+  CKR(launch_ex(h, gn_finalize_kernel, dim3((R.nb * 8 + 127) / 128), dim3(128), 0, s, 1, stats + (long long)R.b0 * 16,
+                (const double*)gn.bias_gsum, (const UttTable*)R.utt + R.b0, R.nb, C / 8, mr + (long long)R.b0 * 8));
   if (fuse_ln) {
     if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, mr, resid, *fuse_ln, s);
     return launch_gn_ln<float, true>(h, R, gn, mr, resid, *fuse_ln, s);
@@ -613,21 +666,21 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
   const int I = h->inner(), D = h->cfg.head_dim;
   const float scale = 1.0f / sqrtf((float)D);
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
-  if (tc) return launch_attn_tc(h->encode, R.qkv, 3LL * I, I, R.M, R.utt, R.work, R.n_work, R.ao, I, scale, s, &h->err, h->attn_prof, h->pdl != 0);
+  if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl != 0);
   if (h->bf) {
     if (D == 64)
-      attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
-                                                          static_cast<bf16*>(R.ao), I, scale);
+      attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
+                                                          static_cast<bf16*>(R.ao_all), I, scale);
     else
-      attn_simt_kernel<bf16, 32><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv), 3LL * I, I, R.utt, R.work,
-                                                          static_cast<bf16*>(R.ao), I, scale);
+      attn_simt_kernel<bf16, 32><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
+                                                          static_cast<bf16*>(R.ao_all), I, scale);
   } else {
     if (D == 64)
-      attn_simt_kernel<float, 64><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv), 3LL * I, I, R.utt, R.work,
-                                                           static_cast<float*>(R.ao), I, scale);
+      attn_simt_kernel<float, 64><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
+                                                           static_cast<float*>(R.ao_all), I, scale);
     else
-      attn_simt_kernel<float, 32><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv), 3LL * I, I, R.utt, R.work,
-                                                           static_cast<float*>(R.ao), I, scale);
+      attn_simt_kernel<float, 32><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
+                                                           static_cast<float*>(R.ao_all), I, scale);
   }
   CK(cudaGetLastError());
   return 0;
@@ -695,20 +748,26 @@ int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void
   return 0;
 }
 
-// One estimator evaluation + the ODE stage update fused in final_proj's epilogue.
-int emit_nfe(cfm_handle* h, Plan* pl, int nfe_index, const OdeStage& st, float* out_f32_override, cudaStream_t s) {
+// One estimator evaluation of one lane + the ODE stage update fused in final_proj's epilogue.
+int emit_nfe(cfm_handle* h, Plan* pl, const LaneDef& ln, int nfe_index, const OdeStage& st, float* out_f32_override, cudaStream_t s) {
   const int C = h->C(), F = h->cfg.out_channels, es = h->es;
   const Model& m = h->model;
-  Res R1 = res_of(pl, 0), R2 = res_of(pl, 1);
+  Res R1 = res_of(h, pl, 0, ln), R2 = res_of(h, pl, 1, ln);
+  const long long row0 = 2LL * ln.r2;  // first full-resolution row of the lane
   h->launch_counter++;
-  CK(cudaMemsetAsync(pl->stats, 0, pl->stats_bytes, s));
+  {  // zero the lane's GroupNorm sums of every site: stats is [site][B][16] doubles
+    const int n_sites = 2 * (4 + h->cfg.n_mid_blocks) + 1;
+    CK(cudaMemset2DAsync(pl->stats + (long long)ln.b0 * 16, (size_t)pl->B * 16 * sizeof(double), 0, (size_t)ln.nb * 16 * sizeof(double),
+                         n_sites, s));
+  }
   int site = 0;
   int stage_i = 0;
   const int n_res = 4 + h->cfg.n_mid_blocks;
   auto tproj = [&](int r) { return pl->tproj + ((long long)nfe_index * n_res + r) * C; };
+  void* xin = act_off(pl->xin, row0 * pl->xin_ld, es);
 
   // down 0 (full resolution): [x | mu] -> X1; masked copy of the stage output -> right half of cat1 (skip h0)
-  CKR(run_stage(h, pl, R1, m.stages[stage_i], pl->xin, pl->xin_ld, site, tproj(stage_i), act_off(R1.cat, C, es), 2 * C, s));
+  CKR(run_stage(h, pl, R1, m.stages[stage_i], xin, pl->xin_ld, site, tproj(stage_i), act_off(R1.cat, C, es), 2 * C, s));
   stage_i++;
   {  // Downsample1D: Conv1d k3 s2 p1 on the masked skip, rows viewed in pairs [M2, 4C]
     const int shifts[3] = {-1, 0, 0};
@@ -763,15 +822,15 @@ int emit_nfe(cfm_handle* h, Plan* pl, int nfe_index, const OdeStage& st, float* 
     p.ld_k = F;
     for (int j = 0; j < 3; ++j) {
       p.c_k[j] = st.c_k[j];
-      p.kin[j] = st.kin[j] >= 0 ? pl->kbuf[st.kin[j]] : nullptr;
+      p.kin[j] = st.kin[j] >= 0 ? pl->kbuf[st.kin[j]] + row0 * F : nullptr;
     }
-    p.kout = st.kout >= 0 ? pl->kbuf[st.kout] : nullptr;
+    p.kout = st.kout >= 0 ? pl->kbuf[st.kout] + row0 * F : nullptr;
     if (out_f32_override) {  // bare estimator call: v itself
-      p.resid = nullptr, p.out_f32 = out_f32_override, p.ld_f32 = F, p.out_act = nullptr;
+      p.resid = nullptr, p.out_f32 = out_f32_override + row0 * F, p.ld_f32 = F, p.out_act = nullptr;
     } else {
-      p.resid = pl->xstate, p.ld_resid = F;
-      p.out_f32 = st.write_state ? pl->xstate : nullptr, p.ld_f32 = F;
-      p.out_act = pl->xin, p.ld_act = pl->xin_ld;
+      p.resid = pl->xstate + row0 * F, p.ld_resid = F;
+      p.out_f32 = st.write_state ? pl->xstate + row0 * F : nullptr, p.ld_f32 = F;
+      p.out_act = xin, p.ld_act = pl->xin_ld;
     }
     CKR(launch_gemm(h, p, true, s));
   }
@@ -837,10 +896,31 @@ int emit_unpack(cfm_handle* h, Plan* pl, const float* state, const float* fill, 
   return 0;
 }
 
+// Runs fn(lane, stream) for every lane: lane 0 on `s`, the others on the handle's lane streams, forked from and joined
+// back into `s` with events (inside a stream capture this makes the lanes parallel branches of the graph).
+template <typename Fn>
+int for_each_lane(cfm_handle* h, Plan* pl, cudaStream_t s, Fn&& fn) {
+  const int n = (int)pl->lanes.size();
+  if (n > 1) {
+    CK(cudaEventRecord(h->fork_event, s));
+    for (int i = 1; i < n; ++i) CK(cudaStreamWaitEvent(h->lane_streams[i - 1], h->fork_event, 0));
+  }
+  int r = 0;
+  for (int i = 0; i < n && r == 0; ++i) r = fn(pl->lanes[i], i == 0 ? s : h->lane_streams[i - 1]);
+  for (int i = 1; i < n; ++i) {  // always join, so that a failed capture does not leave unjoined streams behind
+    cudaError_t e1 = cudaEventRecord(h->lane_events[i - 1], h->lane_streams[i - 1]);
+    cudaError_t e2 = cudaStreamWaitEvent(s, h->lane_events[i - 1], 0);
+    if (r == 0 && (e1 != cudaSuccess || e2 != cudaSuccess)) r = fail(h, CFM_ERR_CUDA, "lane join failed");
+  }
+  return r;
+}
+
 int emit_ode_loop(cfm_handle* h, Plan* pl, cudaStream_t s) {
   CKR(emit_time_embedding(h, pl, (int)pl->stages.size(), pl->tvals, s));
-  for (size_t j = 0; j < pl->stages.size(); ++j) CKR(emit_nfe(h, pl, (int)j, pl->stages[j], nullptr, s));
-  return 0;
+  return for_each_lane(h, pl, s, [&](const LaneDef& ln, cudaStream_t ls) -> int {
+    for (size_t j = 0; j < pl->stages.size(); ++j) CKR(emit_nfe(h, pl, ln, (int)j, pl->stages[j], nullptr, ls));
+    return 0;
+  });
 }
 
 int build_stages(cfm_handle* h, Plan* pl, const float* t_span, int n_points, int solver) {
@@ -925,6 +1005,9 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("CFM_B200_PDL")) h->pdl = atoi(e) != 0;
   if (const char* e = getenv("CFM_B200_PAIR")) h->pair_mode = atoi(e);  // 0 never, 1 long-K GEMMs (default), 2 always
+  if (const char* e = getenv("CFM_B200_TMA_EPI")) h->tma_epi = atoi(e);
+  if (const char* e = getenv("CFM_B200_LANES")) h->lanes_req = std::max(1, std::min(16, atoi(e)));
+  if (const char* e = getenv("CFM_B200_LANE_MIN_ROWS")) h->lane_min_rows = std::max(1, atoi(e));
   if (const char* e = getenv("CFM_B200_CLUSTER")) {
     const int c = atoi(e);
     if (c == 1 || c == 2 || c == 4) h->cluster = c;
@@ -967,6 +1050,9 @@ void cfm_destroy(cfm_handle* h) {
   free_arena(h->wallocs);
   if (h->ws_base) cudaFree(h->ws_base);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (cudaStream_t st : h->lane_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->lane_events) cudaEventDestroy(ev);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   delete h;
 }
 
@@ -1059,8 +1145,10 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   pl->M2 = s2, pl->M1 = 2 * s2;
   std::vector<int> i1(pl->M1, 0), i2(pl->M2, 0);
   std::vector<int4> w1, w2;
+  std::vector<int> wfirst1(batch + 1, 0), wfirst2(batch + 1, 0);
   const int QT = 128;
   for (int b = 0; b < batch; ++b) {
+    wfirst1[b] = (int)w1.size(), wfirst2[b] = (int)w2.size();
     for (int r = 0; r < 2; ++r) {
       const UttTable& u = r == 0 ? u1[b] : u2[b];
       std::vector<int>& info = r == 0 ? i1 : i2;
@@ -1077,6 +1165,44 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     }
   }
   pl->n_work1 = (int)w1.size(), pl->n_work2 = (int)w2.size();
+  wfirst1[batch] = pl->n_work1, wfirst2[batch] = pl->n_work2;
+  {  // ---- lanes: contiguous utterance groups of equal estimated cost  L (274 C^2 + 1800 C) + 24 C L^2  
+    int n_lanes = std::max(1, std::min(h->lanes_req, batch));
+    n_lanes = std::max(1, std::min(n_lanes, pl->M1 / std::max(1, h->lane_min_rows)));
+    if (h->stop_after >= 0) n_lanes = 1;  // the debug launch counter is meaningful for a single chain only
+    const double Cd = h->C();
+    std::vector<double> cum(batch + 1, 0.0);
+    for (int b = 0; b < batch; ++b) {
+      const double L = lengths[b];
+      cum[b + 1] = cum[b] + L * (274.0 * Cd * Cd + 1800.0 * Cd) + 24.0 * Cd * L * L;
+    }
+    pl->lanes.clear();
+    int b0 = 0;
+    for (int i = 0; i < n_lanes; ++i) {
+      int b1 = batch;
+      if (i + 1 < n_lanes) {
+        const double target = cum[batch] * (i + 1) / n_lanes;
+        b1 = b0 + 1;
+        while (b1 < batch - (n_lanes - 1 - i) && fabs(cum[b1 + 1] - target) <= fabs(cum[b1] - target)) ++b1;
+      }
+      LaneDef ln;
+      ln.b0 = b0, ln.nb = b1 - b0;
+      ln.r2 = u2[b0].start;
+      ln.m2 = (b1 < batch ? u2[b1].start : pl->M2) - ln.r2;
+      ln.w0[0] = wfirst1[b0], ln.nw[0] = wfirst1[b1] - wfirst1[b0];
+      ln.w0[1] = wfirst2[b0], ln.nw[1] = wfirst2[b1] - wfirst2[b0];
+      pl->lanes.push_back(ln);
+      b0 = b1;
+    }
+    while ((int)h->lane_streams.size() + 1 < n_lanes) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      h->lane_streams.push_back(st), h->lane_events.push_back(ev);
+    }
+    if (!h->fork_event) CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+  }
   {  // size the persistent workspace arena for this plan (tables + state + activations + host-path staging)
     const size_t C_ = h->C(), I_ = h->inner(), F_ = h->cfg.out_channels, es_ = h->es, M1_ = pl->M1, M2_ = pl->M2;
     const size_t nt = pl->stages.size(), nres = 4 + h->cfg.n_mid_blocks;
@@ -1203,7 +1329,7 @@ int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float
   st.t = t, st.c_v = 1.f, st.kout = -1, st.write_state = false;
   for (int j = 0; j < 3; ++j) st.c_k[j] = 0.f, st.kin[j] = -1;
   h->launch_counter = 0;
-  CKR(emit_nfe(h, pl, 0, st, pl->vout, s));
+  CKR(for_each_lane(h, pl, s, [&](const LaneDef& ln, cudaStream_t ls) -> int { return emit_nfe(h, pl, ln, 0, st, pl->vout, ls); }));
   CKR(emit_unpack(h, pl, pl->vout, nullptr, v, s));
   // restore the planned time grid for subsequent solves
   std::vector<float> tv(pl->stages.size());
@@ -1282,6 +1408,23 @@ int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max
 int cfm_set_speakers(cfm_handle* h, const float* spks_dev) {
   if (!h) return CFM_ERR_INVALID;
   h->spks = spks_dev;
+  return 0;
+}
+
+int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows) {
+  if (!h || lanes < 1 || lanes > 16) return fail(h, CFM_ERR_INVALID, "lanes must be in [1, 16]");
+  h->lanes_req = lanes;
+  if (min_rows > 0) h->lane_min_rows = min_rows;
+  return 0;
+}
+
+int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
+  if (!h || !key) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (strcmp(key, "tma_epi") == 0) h->tma_epi = value == 1 ? 0x3f : value;
+  else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
+  else if (strcmp(key, "pdl") == 0) h->pdl = value != 0;
+  else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
+  else return fail(h, CFM_ERR_INVALID, "unknown option '%s' or value %d out of range", key, (int)value);
   return 0;
 }
 

@@ -75,6 +75,7 @@ struct GemmParams {
   long long ld_k;
   int cluster;  // CTAs per cluster sharing one weight tile via TMA multicast (1, 2 or 4)
   int pair;     // 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 per pair)
+  int tma_epi;  // 1: epilogue_tile_tma (row-per-thread math, swizzled smem staging, TMA store / reduce-add); see launch_gemm
   unsigned long long* prof;  // debug: CTA 0 writes per-role cycle counters (see gemm_tc_kernel); nullptr = off
 };
 
@@ -655,6 +656,116 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-store epilogue (modes STORE / SNAKE / MASK -> bf16, RESID without activation copy -> fp32 add into the stream).
+// tcgen05.ld gives each thread one accumulator row; instead of transposing through smem to get coalesced global accesses,
+// the thread applies the epilogue math to its own row (column constants come from uniform, L1-resident __ldg), writes
+// the converted row into a swizzled staging tile and one lane hands the 32 x 32 unit to the TMA engine:
+//   bf16 : 32 rows x 64 B, SWIZZLE_64B, two units in flight per warp         (cp.async.bulk.tensor store)
+//   fp32 : 32 rows x 128 B, SWIZZLE_128B, x += acc + bias done by L2         (cp.reduce.async.bulk.tensor .add)
+// Per 128 x BN tile this moves 128*BN*2 (bf16) bytes into smem once and lets TMA read them once - no ld.shared, no
+// st.global, no residual load - against write + read of an fp32 tile plus per-row global instructions in epilogue_tile;
+// the GEMMs are shared-memory-bandwidth bound, so the staging bytes are what the epilogue costs.
+// The accumulator is released (`release()`) as soon as the warp's last tcgen05.ld has completed, before the stores drain.
+template <int BN, int MODE, typename Release>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tm_out, uint32_t taddr, uint32_t stg,
+                                                  int m0, int n0, int half, int lane, Release&& release) {
+  constexpr int UNITS = BN / 32;
+  constexpr bool F32 = (MODE == EPI_RESID);
+  constexpr int UNIT_BYTES = F32 ? 4096 : 2048;
+  constexpr int GROUP = 8192 / UNIT_BYTES;  // units staged per fence / TMA-issue round (per-warp staging = 8 KB)
+  bool valid = true;
+  if constexpr (MODE == EPI_MASK) valid = (load_row_info(p, m0 + lane) & ROW_VALID) != 0;
+  uint32_t ra[16], rb[16];
+  bool released = false;
+  if (half < UNITS) {
+    ptx::tmem_ld16(taddr + half * 32, ra);
+    ptx::tmem_ld16(taddr + half * 32 + 16, rb);
+  }
+  int staged = 0;        // units staged and not yet handed to the TMA engine
+  int first_n = 0;       // first column of the oldest staged unit (staged units are 64 columns apart)
+  auto flush = [&]() {   // generic-proxy smem writes -> async proxy, then one lane issues the stores of this round
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 0; i < staged; ++i) {
+        if constexpr (F32) ptx::tma_reduce_add_2d(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
+        else ptx::tma_store_2d(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
+      }
+      ptx::bulk_commit();
+    }
+    staged = 0;
+  };
+#pragma unroll 1
+  for (int u = half; u < UNITS; u += 2) {
+    const int n = n0 + u * 32;
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]), v[16 + i] = __uint_as_float(rb[i]);
+    if (u + 2 < UNITS) {  // next unit's accumulators travel while this one is converted and staged
+      ptx::tmem_ld16(taddr + (u + 2) * 32, ra);
+      ptx::tmem_ld16(taddr + (u + 2) * 32 + 16, rb);
+    } else {
+      release();
+      released = true;
+    }
+    if (n >= p.N || m0 >= p.M) continue;  // warp-uniform
+    // ---- epilogue math on this thread's row; columns >= N are clipped by the TMA store
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (n + i < p.N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+          v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+        }
+      }
+    }
+    if constexpr (MODE == EPI_SNAKE) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (n + i < p.N) {
+          const float4 ea = __ldg(reinterpret_cast<const float4*>(p.ea + n + i));
+          const float4 ib = __ldg(reinterpret_cast<const float4*>(p.ib + n + i));
+          const float s0 = ActIO<bf16>::fsin(v[i] * ea.x), s1 = ActIO<bf16>::fsin(v[i + 1] * ea.y);
+          const float s2 = ActIO<bf16>::fsin(v[i + 2] * ea.z), s3 = ActIO<bf16>::fsin(v[i + 3] * ea.w);
+          v[i] = fmaf(s0 * s0, ib.x, v[i]), v[i + 1] = fmaf(s1 * s1, ib.y, v[i + 1]);
+          v[i + 2] = fmaf(s2 * s2, ib.z, v[i + 2]), v[i + 3] = fmaf(s3 * s3, ib.w, v[i + 3]);
+        }
+      }
+    }
+    if constexpr (MODE == EPI_MASK) {
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+    }
+    // ---- stage; before the first write of a round the previous round's stores must have read the staging area
+    if (staged == 0) {
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
+      first_n = n;
+    }
+    const uint32_t buf = stg + staged * UNIT_BYTES;
+    if constexpr (F32) {
+      const uint32_t row = buf + lane * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ptx::sts128(row + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    } else {
+      const uint32_t row = buf + lane * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint2 lo = pack4_bf16(v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3]);
+        const uint2 hi = pack4_bf16(v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]);
+        ptx::sts128_u32(row + ((c ^ ((lane >> 1) & 3)) << 4), lo.x, lo.y, hi.x, hi.y);
+      }
+    }
+    if (++staged == GROUP) flush();
+  }
+  if (staged > 0) flush();
+  if (!released) release();
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 implementation.
 template <int BN>
 struct TcCfg {
@@ -666,7 +777,8 @@ struct TcCfg {
   static constexpr int CTRL_BYTES = 2048;  // mbarriers + TMEM slot (256 B), GroupNorm partial sums [2 sets][8 warps][8 groups][2] + counters
   static constexpr int N_EPI_WARPS = 8;
   static constexpr int EPI_LD = 36;  // padded row (floats): 16-byte aligned rows, conflict-free 128-bit accesses
-  static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;     // per-warp staging for the coalesced epilogue
+  static constexpr int EPI_WARP_BYTES = 8192;  // per-warp staging: 32 x 36 floats (transposing epilogue) or 1024-aligned TMA-store units
+  static constexpr int EPI_BYTES = N_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + CTRL_BYTES + EPI_BYTES;
@@ -690,7 +802,7 @@ __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, b
 template <int BN>
 __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -720,6 +832,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::prefetch_tmap(&tmA0);
     ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmW);
+    if (p.tma_epi) ptx::prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -818,12 +931,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // tcgen05.ld hands each thread one accumulator ROW; touching global memory in that shape makes every warp
     // instruction hit 32 different cache lines, so each 32x32 block goes through a per-warp smem tile (epi_block).
     // The mode switch is hoisted out of all loops: each mode runs its own specialised copy of the loop.
-    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * 32 * Cfg::EPI_LD * 4;
+    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * Cfg::EPI_WARP_BYTES;
     auto run = [&](auto mode_tag) {
       constexpr int MODE = decltype(mode_tag)::value;
       const int q = warp & 3;            // TMEM lane quarter this warp may touch
       const int half = (warp - 4) >> 2;  // the two warps of a quarter alternate over the 32-column blocks
       const int cg = lane & 7;
+      (void)cg;
       int local = 0;
       const bool prof = p.prof != nullptr && blockIdx.x == 0 && warp == 4;
       unsigned long long w_tfull = 0;
@@ -835,11 +949,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK || MODE == EPI_RESID) {
+          if (p.tma_epi) {
+            epilogue_tile_tma<BN, MODE>(p, &tmOut, taddr, stg, m0, n0, half, lane, [&] {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            });
+            continue;
+          }
+        }
         epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       }
+      if (p.tma_epi && lane == 0) ptx::bulk_wait_all();  // smem staging is read / global writes land before the CTA exits
       if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
     };
     switch (p.mode) {
@@ -881,7 +1006,8 @@ struct Tc2Cfg {
   static constexpr int CTRL_BYTES = 2048;
   static constexpr int N_EPI_WARPS = 8;
   static constexpr int EPI_LD = 36;
-  static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int EPI_WARP_BYTES = 8192;
+  static constexpr int EPI_BYTES = N_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + CTRL_BYTES + EPI_BYTES;
@@ -893,7 +1019,7 @@ struct Tc2Cfg {
 template <int BN>
 __global__ void __launch_bounds__(Tc2Cfg<BN>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
   using Cfg = Tc2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -918,6 +1044,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     ptx::prefetch_tmap(&tmA0);
     ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmW);
+    if (p.tma_epi) ptx::prefetch_tmap(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -1006,12 +1133,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
-    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * 32 * Cfg::EPI_LD * 4;
+    const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * Cfg::EPI_WARP_BYTES;
     auto run = [&](auto mode_tag) {
       constexpr int MODE = decltype(mode_tag)::value;
       const int q = warp & 3;
       const int half = (warp - 4) >> 2;
       const int cg = lane & 7;
+      (void)cg;
       int local = 0;
       const bool prof = p.prof != nullptr && blockIdx.x == 0 && warp == 4;
       unsigned long long w_tfull = 0;
@@ -1023,6 +1151,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK || MODE == EPI_RESID) {
+          if (p.tma_epi) {
+            epilogue_tile_tma<BN, MODE>(p, &tmOut, taddr, stg, m0, n0, half, lane, [&] {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+              }
+            });
+            continue;
+          }
+        }
         epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
         ptx::tc_fence_before();
         __syncwarp();
@@ -1031,6 +1172,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
         }
       }
+      if (p.tma_epi && lane == 0) ptx::bulk_wait_all();
       if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
     };
     switch (p.mode) {

@@ -216,6 +216,58 @@ def test_utterances_are_independent_given_T(flags, tol):
     assert rel_l2(solo[0], full[1]) <= tol
 
 
+@pytest.mark.parametrize("tma_mask,pair_mode", [(0, 0), (0, 2), (63, 1), (63, 2), (4, 1)])
+def test_kernel_selection_switches_keep_parity(tma_mask, pair_mode):
+    """cfm_set_option: every GEMM epilogue / CTA-pair selection (TMA-store epilogue per mode incl. the L2 reduce-add residual,
+    1-CTA vs cta_group::2 kernels) stays within the bf16 tolerance of the oracle on the prod estimator."""
+    ora, m = pair(syn.PROD, "euler", "bf16")
+    lengths = [150, 97, 200, 31]
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=5)
+    ts = torch.linspace(0, 1, 5)
+    ref = ora.solve(z, ts, mu, mask)
+    m.refresh(torch.device("cuda", torch.cuda.current_device()))
+    m.set_option("tma_epi", tma_mask)
+    m.set_option("pair_mode", pair_mode)
+    out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
+    check(out, ref, "bf16", f"prod euler/4 tma_mask={tma_mask} pair_mode={pair_mode}")
+    with pytest.raises(ValueError):
+        m.set_option("no_such_switch", 1)
+
+
+@pytest.mark.parametrize("lanes", [2, 3, 5])
+def test_lanes_are_invisible_in_the_result(lanes):
+    """cfm_set_lanes: the batch is cut into utterance groups that run as parallel graph branches.  Against the oracle
+    (fp32 mode, rk4 so that the k-buffers are exercised, ragged batch), and bitwise against the single-lane decode on the
+    tensor-core path with the order-independent statistics pass."""
+    lengths = [70, 45, 128, 3, 99, 128, 17]
+    ora, m = pair(TINY64, "rk4", "fp32")
+    m.set_lanes(lanes, 1)
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=3, T=128)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
+    check(out, ref, "fp32", f"rk4/2 lanes={lanes}")
+    with torch.inference_mode():
+        v_ref = ora.estimator(z, mask, mu, torch.tensor(0.4))
+    v = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), torch.tensor(0.4))
+    assert rel_l2(v, v_ref) <= FP32_TIGHT
+    m.close()
+    for flags in (N.FLAG_UNFUSED_STATS, N.FLAG_UNFUSED_STATS | N.FLAG_NO_GRAPH, 0):
+        _, mb = pair(syn.PROD, "midpoint", "bf16", flags)
+        lengths = [200, 123, 198, 57, 156, 111]
+        mu, mask, z, _ = syn.make_inputs(lengths, seed=9, T=200)
+        ts = torch.linspace(0, 1, 3).cuda()
+        mb.set_lanes(1, 1)
+        one = mb.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+        mb.set_lanes(lanes, 1)
+        many = mb.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+        if flags & N.FLAG_UNFUSED_STATS:
+            assert torch.equal(one, many), flags
+        else:
+            assert rel_l2(many, one) <= TOL["bf16"]
+        mb.close()
+
+
 def test_bf16_mode_tracks_fp32_mode_at_cfg2_length():
     """Beyond oracle-sized inputs the fp32 CUDA mode (itself oracle-checked above) is the reference for the
     tensor-core mode: 10 s utterances (L=938) of BASELINE config 2, prod estimator, 10 Euler steps."""

@@ -156,6 +156,71 @@ def c_time():
               f"finite={bool(torch.isfinite(out).all())} info={m.plan_info()}")
 
 
+def c_epimodes():
+    """cfg2 decode time against which epilogue modes use the TMA-store epilogue (bit m = EpiMode m) and the pair policy."""
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16").eval().cuda()
+    P.synthetic.fill_named_seed(m.estimator, 1234)
+    m.refresh(torch.device("cuda", 0))
+    lengths = P.synthetic.config_lengths(os.environ.get("DIAG_WORKLOAD", "cfg2"))
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+    ts = torch.linspace(0, 1, 11, device="cuda")
+    combos = os.environ.get("DIAG_COMBOS", "0:1,1:1,4:1,8:1,16:1,63:1,63:2,0:2,0:0")
+    for item in combos.split(","):
+        tma, pair = (int(v) for v in item.split(":"))
+        m.set_option("tma_epi", tma)
+        m.set_option("pair_mode", pair)
+        for _ in range(2):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            out = m.solve(z, ts, mu, mask, lengths=lengths)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"[epimodes tma_mask={tma} pair_mode={pair}] {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s "
+              f"finite={bool(torch.isfinite(out).all())}", flush=True)
+
+
+def c_lanes():
+    """Decode time of cfg2 / cfg3 / cfg4 against the number of lanes (parallel graph branches)."""
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16").eval().cuda()
+    P.synthetic.fill_named_seed(m.estimator, 1234)
+    names = os.environ.get("DIAG_WORKLOADS", "cfg2,cfg4,cfg3").split(",")
+    for name in names:
+        lengths = P.synthetic.config_lengths(name)
+        mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+        ts = torch.linspace(0, 1, 11, device="cuda")
+        ref = None
+        for lanes in [int(v) for v in os.environ.get("DIAG_LANES", "1,2,3,4,6").split(",")]:
+            m.set_lanes(lanes, 2048)
+            for _ in range(2):
+                out = m.solve(z, ts, mu, mask, lengths=lengths)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5 if name != "cfg3" else 2
+            e0.record()
+            for _ in range(reps):
+                out = m.solve(z, ts, mu, mask, lengths=lengths)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            fl = P.synthetic.algorithmic_flops(lengths, 384, 10)
+            if ref is None:
+                ref = out.clone()
+            print(f"[lanes {name} lanes={lanes}] {ms:.2f} ms/solve  {sum(lengths)/ms*1e3:.3e} frames/s  {fl/ms/1e9:.1f} TFLOP/s "
+                  f"rel_vs_1lane={rel(out, ref):.2e} finite={bool(torch.isfinite(out).all())} kernels={m.plan_info()['kernels_per_solve']}", flush=True)
+
+
 def c_trace():
     """Bisect the schedule: compare intermediate buffers (fp32 mode, SIMT kernels, 7 launches per resnet / block)
     against hooks on the dense oracle.  Valid rows per utterance (+ the pad-token row for the residual stream)."""
@@ -341,6 +406,9 @@ def c_gemmprof():
     lib, h = m._lib, m._handle
     g = torch.Generator().manual_seed(0)
     M = 30144
+    for key in ("tma_epi", "pair_mode"):
+        if os.environ.get("DIAG_" + key.upper()) is not None:
+            m.set_option(key, int(os.environ["DIAG_" + key.upper()]))
     shapes = [("QKV bf16", 1152, 384, 1, 0), ("QKV f32out", 1152, 384, 1, 1), ("out-proj resid", 384, 384, 1, 2), ("out-proj f32", 384, 384, 1, 1),
               ("out-proj bf16", 384, 384, 1, 0), ("conv2 f32", 384, 384, 3, 1), ("conv2 f32+stats", 384, 384, 3, 3), ("conv2 bf16", 384, 384, 3, 0), ("FF2 resid", 384, 1536, 1, 2),
               ("FF2 bf16", 384, 1536, 1, 0), ("FF1 bf16", 1536, 384, 1, 0)]
@@ -370,6 +438,54 @@ def c_gemmprof():
         fl = 2.0 * M * N * K * taps
         print(f"[gemmprof {name:16s} N={N} K={K}x{taps}] {us:7.1f} us {fl/us/1e6:7.1f} TFLOP/s | tiles(cta0)={pr[8]} prod tot={pr[0]} wait_empty={pr[1]} | "
               f"mma tot={pr[2]} wait_full={pr[3]} wait_tempty={pr[4]} | epi tot={pr[5]} wait_tfull={pr[6]}")
+
+
+def c_tmaepi():
+    """TMA-store epilogue vs the transposing epilogue: results (bf16 store, in-place fp32 residual add) and stand-alone
+    timings for the cfg2 GEMM shapes, 1-CTA and CTA-pair kernels."""
+    import torch
+    import matcha_tts_24k_b200 as P
+    ora, m = _models(TINY, "euler", "bf16", 1)
+    m.refresh(torch.device("cuda", 0))
+    lib, h = m._lib, m._handle
+    g = torch.Generator().manual_seed(0)
+    shapes = [("QKV", 1152, 384, 1, 0), ("FF1-store", 1536, 384, 1, 0), ("out-proj resid", 384, 384, 1, 2), ("FF2 resid", 384, 1536, 1, 2),
+              ("conv bf16", 384, 384, 3, 0), ("N=320 resid", 320, 320, 1, 2), ("N=1280 store", 1280, 320, 1, 0), ("N=960 store", 960, 320, 1, 0)]
+    for M in (30144, 1000):
+        for name, N, K, taps, mode in shapes:
+            a = torch.randn(M, K, generator=g).bfloat16().cuda()
+            w = (torch.randn(taps * N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+            shifts = [0] if taps == 1 else [-1, 0, 1]
+            sh = (C.c_int32 * taps)(*shifts)
+            base = torch.randn(M, N, generator=g).cuda()
+            outs = {}
+            line = f"[tmaepi M={M} {name:14s} N={N} K={K}x{taps}]"
+            for tma in (0, 1):
+                for pair in (0, 2):
+                    m.set_option("tma_epi", tma)
+                    m.set_option("pair_mode", pair)
+                    d32 = base.clone()
+                    d16 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+                    call = lambda: P.native.check(lib, h, lib.cfm_debug_gemm_profile(h, a.data_ptr(), w.data_ptr(), d32.data_ptr(), d16.data_ptr(),
+                                                                                   M, N, K, taps, sh, mode, None, None))
+                    call()
+                    torch.cuda.synchronize()
+                    outs[(tma, pair)] = (d16.float() if mode == 0 else d32).clone()
+                    for _ in range(3):
+                        call()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(20):
+                        call()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    us = e0.elapsed_time(e1) / 20 * 1e3
+                    line += f" | tma={tma} pair={pair}: {us:6.1f} us {2.0 * M * N * K * taps / us / 1e6:6.1f} TF"
+            ref = outs[(0, 0)]
+            worst = max(rel(v, ref) for v in outs.values())
+            exact = all(torch.equal(v, ref) for v in outs.values())
+            print(line + f" | worst rel vs old={worst:.2e} bitwise={exact} finite={bool(torch.isfinite(ref).all())}", flush=True)
 
 
 def c_attnprof():
