@@ -3,11 +3,13 @@
 // One CTA per (utterance, head, 128-query tile); 192 threads = TMA warp, MMA warp, 4 softmax warps (one query row per
 // thread).  Keys are processed in 64-key tiles through a software pipeline:
 //     S_j  = Q K_j^T    tcgen05.mma M128 N64 K64  (Q, K tiles K-major, 128B-swizzled by TMA)  -> TMEM S[j & 1]
-//     P_j  = exp2(...)  tcgen05.ld S_j -> registers -> online softmax -> bf16 P_j in smem P[j & 1] (UMMA K-major layout)
-//     PV_j = P_j V_j    tcgen05.mma M128 N64 K64  (V tile MN-major straight from TMA)         -> TMEM PV
-//     O   += PV_{j-1}   consumed one iteration late, in registers (packed fp32x2)
+//     P_j  = exp2(...)  tcgen05.ld S_j -> registers (once) -> softmax -> bf16 P_j in smem P[j & 1] (UMMA K-major layout)
+//     O   += P_j V_j    tcgen05.mma M128 N64 K64  (V tile MN-major straight from TMA), accumulated IN TMEM
 // S, P, K and V are double-buffered, so S_{j+1} is computed while the softmax of tile j runs and the softmax warps never
-// wait on an MMA issued in the same iteration.  Two CTAs per SM (80 KB smem, 256 TMEM columns each).
+// wait on an MMA issued in the same iteration.  The running maximum is updated lazily (only when a tile's maximum exceeds
+// the reference by more than 2^8, FlashAttention-4 style): P and the row sum stay relative to the same reference, so the
+// result is unchanged, and O is touched by the softmax warps only on those rare rescales (tcgen05.ld / mul / tcgen05.st)
+// and once at the end.  Two CTAs per SM (80 KB smem, 256 TMEM columns each).
 // The per-key bias implements the reference's additive float mask in the packed formulation (attn.cuh header).
 #pragma once
 #include <cuda.h>
@@ -65,93 +67,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
-}
-
-// Row maximum of this thread's 64 raw scores (TMEM columns [taddr, taddr + 64)).  RAGGED: key index >= L is either the
-// virtual pad token (key == L, raw bias added) or outside the utterance (-inf).
-template <bool RAGGED>
-__device__ __forceinline__ float attn_rowmax(uint32_t taddr, int k0, int L, float raw_pad_bias) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < 64; c += 32) {
-    uint32_t a[16], b[16];
-    ptx::tmem_ld16(taddr + c, a);
-    ptx::tmem_ld16(taddr + c + 16, b);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float t[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] = __uint_as_float((i + j) < 16 ? a[i + j] : b[i + j - 16]);
-        if (RAGGED) {
-          const int key = k0 + c + i + j;
-          t[j] = key < L ? t[j] : (key == L ? t[j] + raw_pad_bias : -INFINITY);
-        }
-      }
-      m0 = max3(m0, t[0], t[1]), m1 = max3(m1, t[2], t[3]);
-    }
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
-
-// P = exp2(s * scale_log2 - m) for this thread's 64 columns -> bf16 -> smem in the UMMA K-major 128B-swizzled layout
-// (16-byte chunk c of row r lives at chunk c ^ (r & 7)); returns the row's partial sum.
-template <bool RAGGED>
-__device__ __forceinline__ float attn_exp_store(uint32_t taddr, uint32_t p_row, int r, int k0, int L, float scale_log2,
-                                                float mnew, float pad_bias_log2) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  f32x2 acc01 = pack2(0.f, 0.f), acc23 = pack2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < 64; c += 32) {
-    uint32_t a[16], b[16];
-    ptx::tmem_ld16(taddr + c, a);
-    ptx::tmem_ld16(taddr + c + 16, b);
-    ptx::tmem_ld_wait();
-    float pv[32];
-    if constexpr (!RAGGED) {
-      const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-mnew, -mnew);
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const f32x2 t2 = fma2(pack2(__uint_as_float(i < 16 ? a[i] : b[i - 16]), __uint_as_float(i < 16 ? a[i + 1] : b[i - 15])), sc2, nm2);
-        float t0, t1;
-        unpack2(t2, t0, t1);
-        pv[i] = ex2_approx(t0), pv[i + 1] = ex2_approx(t1);
-        if ((i & 2) == 0) acc01 = add2(acc01, pack2(pv[i], pv[i + 1]));
-        else acc23 = add2(acc23, pack2(pv[i], pv[i + 1]));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float t = fmaf(__uint_as_float(i < 16 ? a[i] : b[i - 16]), scale_log2, -mnew);
-        const int key = k0 + c + i;
-        t = key < L ? t : (key == L ? t + pad_bias_log2 : -INFINITY);
-        pv[i] = ex2_approx(t);
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) s0 += pv[i], s1 += pv[i + 1], s2 += pv[i + 2], s3 += pv[i + 3];
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int chunk = (c >> 3) + g;
-      uint4 pk;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[8 * g + 0], pv[8 * g + 1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[8 * g + 2], pv[8 * g + 3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[8 * g + 4], pv[8 * g + 5]);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[8 * g + 6], pv[8 * g + 7]);
-      pk.x = *reinterpret_cast<uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      pk.z = *reinterpret_cast<uint32_t*>(&h2);
-      pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      ptx::sts128_u32(p_row + ((chunk ^ (r & 7)) << 4), pk.x, pk.y, pk.z, pk.w);
-    }
-  }
-  if constexpr (!RAGGED) {
-    const f32x2 t = add2(acc01, acc23);
-    unpack2(t, s0, s1);
-    return s0 + s1;
-  }
-  return (s0 + s1) + (s2 + s3);
 }
 
 __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
@@ -249,7 +164,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + b * Cfg::P_BYTES + k * 32),
-                         ptx::umma_desc_sw128(v_addr + b * Cfg::V_BYTES + k * 2048), idesc_pv, k > 0);
+                         ptx::umma_desc_sw128(v_addr + b * Cfg::V_BYTES + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         ptx::umma_commit(bar_pv + b);
         if (j + 2 < n_tiles) issue_s(j + 2);
       }
@@ -259,86 +174,124 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
     }
   } else {
-    // ---------------- softmax / correction / epilogue: one query row per thread
+    // ---------------- softmax / rare rescale / epilogue: one query row per thread
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const float pad_bias = u.pad_key_bias * 1.4426950408889634f;
-    f32x2 o2[32];  // 64 output columns as packed fp32 pairs
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o2[d] = pack2(0.f, 0.f);
-    float mrun = -INFINITY, lrun = 0.f;
+    const float raw_pad_bias = u.pad_key_bias / (scale_log2 * 0.6931471805599453f);  // additive mask in raw-score units
+    float mref = -INFINITY, lrun = 0.f;  // exponent reference (log2 domain) and row sum relative to it
     const bool sp = do_prof && warp == 2;
     unsigned long long ws = 0, wbar = 0, wpv = 0;
     const long long ts_start = clock64();
-    auto add_pv = [&](int jprev) {  // O += PV_{jprev}
-      mbar_wait_prof(bar_pv + (jprev & 1), (jprev >> 1) & 1, sp, wpv);
-      ptx::tc_fence_after();
+    uint32_t sv[64];  // raw scores of the current tile (this thread's row)
+    auto load_s = [&](int j) {
+      const uint32_t ts = tmem_base + (j & 1) * 64 + lane_off;
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t a[16], b2[16];
-        ptx::tmem_ld16(tmem_pv + lane_off + c, a);
-        ptx::tmem_ld16(tmem_pv + lane_off + c + 16, b2);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o2[c / 2 + i] = add2(o2[c / 2 + i], pack2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])));
-          o2[c / 2 + 8 + i] = add2(o2[c / 2 + 8 + i], pack2(__uint_as_float(b2[2 * i]), __uint_as_float(b2[2 * i + 1])));
-        }
-      }
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld16(ts + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[c * 16]));
     };
+    mbar_wait_prof(bar_s, 0, sp, ws);
+    ptx::tc_fence_after();
+    load_s(0);
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       const int k0 = j * Cfg::KT;
-      const bool ragged = (k0 + Cfg::KT > L);  // tile holds the pad token and/or rows past this utterance
       const uint32_t p_row = ptx::smem_u32(smem + Cfg::OFF_P + b * Cfg::P_BYTES + r * 128);
-      mbar_wait_prof(bar_s + b, (j >> 1) & 1, sp, ws);
-      ptx::tc_fence_after();
-      const uint32_t ts = tmem_base + b * 64 + lane_off;
-      float mt;
-      if (!ragged) mt = attn_rowmax<false>(ts, k0, L, 0.f);
-      else mt = attn_rowmax<true>(ts, k0, L, pad_bias / scale_log2);
-      const float mnew = fmaxf(mrun, mt * scale_log2);  // finite: key 0 of the first tile is always valid
-      const float corr = ex2_approx(mrun - mnew);
-      float psum;
-      if (!ragged) psum = attn_exp_store<false>(ts, p_row, r, k0, L, scale_log2, mnew, 0.f);
-      else psum = attn_exp_store<true>(ts, p_row, r, k0, L, scale_log2, mnew, pad_bias);
-      if (j > 0) add_pv(j - 1);  // issued an iteration ago: complete by now; frees the PV accumulator for PV_j
-      lrun = lrun * corr + psum;
-      mrun = mnew;
-      if (__any_sync(0xffffffffu, corr != 1.f)) {  // once the running max has settled no row of the warp needs a rescale
-        const f32x2 c2 = pack2(corr, corr);
+      ptx::tmem_ld_wait();
+      if (k0 + Cfg::KT > L) {  // tile holds the pad token and / or rows past this utterance: fix the raw scores in place
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o2[d] = mul2(o2[d], c2);
+        for (int i = 0; i < 64; ++i) {
+          const int key = k0 + i;
+          const float t = __uint_as_float(sv[i]);
+          sv[i] = __float_as_uint(key < L ? t : (key == L ? t + raw_pad_bias : -INFINITY));
+        }
+      }
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      const float mt = fmaxf(m0, m1) * scale_log2;
+      // Lazy reference update: keep mref while the tile maximum stays within 2^8 of it (P <= 256, exact in the final O / l).
+      const bool grow = mt > mref + 8.f;  // j == 0: mref = -inf and key 0 is always valid -> true
+      const float mnew = grow ? mt : mref;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {  // rare: rescale this warp's rows of O (in TMEM) and l
+        const float corr = ex2_approx(mref - mnew);  // 1 for the rows that keep their reference
+        mbar_wait_prof(bar_pv + ((j - 1) & 1), ((j - 1) >> 1) & 1, sp, wpv);  // every PV issued so far has landed in O
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t o[16];
+          ptx::tmem_ld16(tmem_pv + lane_off + c, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          ptx::tmem_st16(tmem_pv + lane_off + c, o);
+        }
+        ptx::tmem_st_wait();
+        lrun *= corr;
+      }
+      mref = mnew;
+      // P = exp2(s * scale - mref) -> bf16 -> smem (UMMA K-major 128B swizzle: 16-byte chunk c of row r at chunk c ^ (r & 7))
+      {
+        const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-mref, -mref);
+        f32x2 acc01 = pack2(0.f, 0.f), acc23 = pack2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const f32x2 t2 = fma2(pack2(__uint_as_float(sv[8 * g + i]), __uint_as_float(sv[8 * g + i + 1])), sc2, nm2);
+            float t0, t1;
+            unpack2(t2, t0, t1);
+            pv[i] = ex2_approx(t0), pv[i + 1] = ex2_approx(t1);
+            if ((i & 2) == 0) acc01 = add2(acc01, pack2(pv[i], pv[i + 1]));
+            else acc23 = add2(acc23, pack2(pv[i], pv[i + 1]));
+          }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]), h1 = __floats2bfloat162_rn(pv[2], pv[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
+          ptx::sts128_u32(p_row + ((g ^ (r & 7)) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+        float s0, s1;
+        unpack2(add2(acc01, acc23), s0, s1);
+        lrun += s0 + s1;
+      }
+      if (j + 1 < n_tiles) {  // S_{j+1} was issued before PV_{j-1}: normally complete by now; its load overlaps the hand-off
+        mbar_wait_prof(bar_s + ((j + 1) & 1), ((j + 1) >> 1) & 1, sp, ws);
+        ptx::tc_fence_after();
+        load_s(j + 1);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::mbar_arrive(bar_p + b);
     }
-    add_pv(n_tiles - 1);
+    mbar_wait_prof(bar_pv + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, sp, wpv);  // O complete
+    ptx::tc_fence_after();
     if (sp && lane == 0) prof[8] = (unsigned long long)(clock64() - ts_start), prof[9] = ws, prof[10] = wbar, prof[11] = wpv;
-    ptx::tc_fence_before();
     const int qi = q0 + r;
-    if (qi < nk) {
-      const float inv = 1.f / lrun;
-      bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
+    const float inv = 1.f / lrun;
+    bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
 #pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        float x[8];
+    for (int c = 0; c < 64; c += 16) {
+      uint32_t a[16];
+      ptx::tmem_ld16(tmem_pv + lane_off + c, a);
+      ptx::tmem_ld_wait();
+      if (qi < nk) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) unpack2(o2[d + i], x[2 * i], x[2 * i + 1]);
-        uint4 pk;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0] * inv, x[1] * inv);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(x[2] * inv, x[3] * inv);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(x[4] * inv, x[5] * inv);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(x[6] * inv, x[7] * inv);
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(dst + 2 * d) = pk;
+        for (int g = 0; g < 2; ++g) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(a[8 * g + 0]) * inv, __uint_as_float(a[8 * g + 1]) * inv);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(a[8 * g + 2]) * inv, __uint_as_float(a[8 * g + 3]) * inv);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(a[8 * g + 4]) * inv, __uint_as_float(a[8 * g + 5]) * inv);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(a[8 * g + 6]) * inv, __uint_as_float(a[8 * g + 7]) * inv);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dst + c + 8 * g) = pk;
+        }
       }
     }
+    ptx::tc_fence_before();
   }
   ptx::tc_fence_before();
   __syncthreads();

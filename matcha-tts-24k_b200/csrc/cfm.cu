@@ -98,7 +98,6 @@ struct Plan {
   float *xstate = nullptr, *vout = nullptr, *kbuf[3] = {nullptr, nullptr, nullptr};
   double* stats = nullptr;
   size_t stats_bytes = 0;
-  float2* gn_mr = nullptr;  // (mean, rstd) per site, utterance, group
   float *stage_mu = nullptr, *stage_z = nullptr, *stage_out = nullptr;  // cfm_solve_host device staging
   // activations per resolution (index 0 = full, 1 = half)
   void* xin = nullptr;
@@ -585,12 +584,12 @@ Res res_of(cfm_handle* h, Plan* pl, int r, const LaneDef& ln) {
 }
 
 template <typename T, bool PRECISE>
-int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const float2* mr, const float* resid, const NormW& ln, cudaStream_t s) {
+int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const double* stats, const float* resid, const NormW& ln, cudaStream_t s) {
   const int C = h->C();
   const int blocks = (R.M * 32 + 255) / 256;
 #define CFM_GN_LN(NCH)                                                                                                     \
   return launch_ex(h, gn_apply_ln_kernel<T, PRECISE, NCH>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, \
-                   R.M, C / 8, (const int*)R.info, mr, (const float*)gn.gamma, (const float*)gn.beta, resid, (long long)C, R.X,   \
+                   R.M, C / 8, (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, resid, (long long)C, R.X,   \
                    (long long)C, (const float*)ln.gamma, (const float*)ln.beta, static_cast<T*>(R.Xn), (long long)C)
   switch (C / 128) {
     case 1: CFM_GN_LN(1);
@@ -605,24 +604,21 @@ int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const float2* mr,
 int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
                  float* out_f32, void* out_act, long long ld_act, cudaStream_t s, const NormW* fuse_ln = nullptr) {
   if (h->stopped()) return 0;
-  h->launch_counter += 2;
+  h->launch_counter++;
   const int C = h->C();
   const double* stats = pl->stats + (long long)site * pl->B * 16;
-  float2* mr = pl->gn_mr + (long long)site * pl->B * 8;
-  CKR(launch_ex(h, gn_finalize_kernel, dim3((R.nb * 8 + 127) / 128), dim3(128), 0, s, 1, stats + (long long)R.b0 * 16,
-                (const double*)gn.bias_gsum, (const UttTable*)R.utt + R.b0, R.nb, C / 8, mr + (long long)R.b0 * 8));
   if (fuse_ln) {
-    if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, mr, resid, *fuse_ln, s);
-    return launch_gn_ln<float, true>(h, R, gn, mr, resid, *fuse_ln, s);
+    if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, stats, resid, *fuse_ln, s);
+    return launch_gn_ln<float, true>(h, R, gn, stats, resid, *fuse_ln, s);
   }
   const long long items = (long long)R.M * (C / 8);
   const int blocks = (int)((items + 255) / 256);
   if (h->bf)
     return launch_ex(h, gn_apply_kernel<bf16, false>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                     (const int*)R.info, (const float2*)mr, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
                      out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
   return launch_ex(h, gn_apply_kernel<float, true>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                   (const int*)R.info, (const float2*)mr, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                   (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
                    out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
 }
 
@@ -648,10 +644,30 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
   return 0;
 }
 
+template <typename T>
+int launch_ln_vec(cfm_handle* h, const Res& R, const NormW& ln, cudaStream_t s) {
+  const int C = h->C();
+  const int blocks = (R.M * 32 + 255) / 256;
+#define CFM_LN_VEC(NCH)                                                                                                        \
+  return launch_ex(h, layernorm_vec_kernel<T, NCH>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.X, (long long)C, R.M,    \
+                   (const float*)ln.gamma, (const float*)ln.beta, static_cast<T*>(R.Xn), (long long)C)
+  switch (C / 128) {
+    case 1: CFM_LN_VEC(1);
+    case 2: CFM_LN_VEC(2);
+    case 3: CFM_LN_VEC(3);
+    default: CFM_LN_VEC(4);
+  }
+#undef CFM_LN_VEC
+}
+
 int run_layernorm(cfm_handle* h, const Res& R, const NormW& ln, cudaStream_t s) {
   if (h->stopped()) return 0;
   h->launch_counter++;
   const int C = h->C();
+  if (C % 128 == 0 && C <= 512) {
+    if (h->bf) return launch_ln_vec<bf16>(h, R, ln, s);
+    return launch_ln_vec<float>(h, R, ln, s);
+  }
   const int blocks = (R.M * 32 + 255) / 256;
   if (h->bf)
     return launch_ex(h, layernorm_kernel<bf16, 16>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.X, (long long)C, R.M, C,
@@ -1138,8 +1154,10 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     const int L = lengths[b], P = t_pad - L, L2 = (L + 1) / 2, T2 = t_pad / 2, P2 = T2 - L2;
     u2[b].start = s2, u2[b].len = L2, u2[b].rows = L2 + 2, u2[b].bias_rows = std::max(P2 - 1, 0), u2[b].t_res = T2;
     u2[b].pad_key_bias = P2 >= 1 ? logf((float)P2) - 1.f : -INFINITY;
+    u2[b].inv_gn_count = 1.0 / ((double)(h->C() / 8) * T2);
     u1[b].start = 2 * s2, u1[b].len = L, u1[b].rows = 2 * (L2 + 2), u1[b].bias_rows = std::max(P - 1, 0), u1[b].t_res = t_pad;
     u1[b].pad_key_bias = P >= 1 ? logf((float)P) - 1.f : -INFINITY;
+    u1[b].inv_gn_count = 1.0 / ((double)(h->C() / 8) * t_pad);
     s2 += L2 + 2;
   }
   pl->M2 = s2, pl->M1 = 2 * s2;
@@ -1246,7 +1264,6 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   const int n_sites = 2 * n_res + 1;
   pl->stats_bytes = (size_t)n_sites * batch * 16 * sizeof(double);
   CKR(plan_alloc(h, pl, reinterpret_cast<void**>(&pl->stats), pl->stats_bytes));
-  CKR(plan_alloc_t(h, pl, &pl->gn_mr, (size_t)n_sites * batch * 8));
   pl->xin_ld = roundup(h->cfg.in_channels, 64);
   CKR(plan_alloc(h, pl, &pl->xin, (size_t)pl->M1 * pl->xin_ld * es));
   for (int r = 0; r < 2; ++r) {

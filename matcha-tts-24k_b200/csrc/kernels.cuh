@@ -19,7 +19,23 @@ struct UttTable {        // one entry per utterance and resolution
   int bias_rows;         // max(P - 1, 0): padded frames whose conv output is exactly the bias
   int t_res;             // padded length T at this resolution (GroupNorm denominator)
   float pad_key_bias;    // log(P) - 1 for the virtual pad token's key, -inf when P == 0
+  double inv_gn_count;   // 1 / (channels per GroupNorm group * t_res)
 };
+
+// (mean, rstd) of GroupNorm group g of utterance b from the fp64 sums: epilogue sums + bias_rows * (sum_c b_c, sum_c b_c^2)
+// for the padded frames that are never materialised (DESIGN.md "pad-aware packing"), over group_ch * t_res elements
+// (reference decoder.py:35-45 normalises over the PADDED length).  Evaluated by every consumer thread itself: 3 fp64
+// operations, which is cheaper than a separate finalize launch between the conv and the apply pass.
+__device__ __forceinline__ float2 gn_mean_rstd(const double* __restrict__ stats, const double* __restrict__ bias_gsum,
+                                               const UttTable* __restrict__ utt, int b, int g) {
+  const double2 st = *reinterpret_cast<const double2*>(stats + ((long long)b * 8 + g) * 2);
+  const double2 bg = __ldg(reinterpret_cast<const double2*>(bias_gsum + g * 2));
+  const double br = (double)__ldg(&utt[b].bias_rows);
+  const double inv = __ldg(&utt[b].inv_gn_count);
+  const double mean = fma(br, bg.x, st.x) * inv;
+  const double var = fmax(fma(-mean, mean, fma(br, bg.y, st.y) * inv), 0.0);
+  return make_float2((float)mean, rsqrtf((float)var + 1e-5f));
+}
 
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)     (reference decoder.py:40 nn.Mish)
@@ -148,7 +164,8 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, const doubl
 // y = valid ? Mish(GN(h)) + addvec[c] : 0;  y += resid[m, c];  -> out_f32 and/or out_act.   8 channels per thread.
 template <typename T, bool PRECISE>
 __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int M, int C, int group_ch,
-                                const int* __restrict__ row_info, const float2* __restrict__ mr,
+                                const int* __restrict__ row_info, const double* __restrict__ stats,
+                                const double* __restrict__ bias_gsum, const UttTable* __restrict__ utt,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ addvec, const float* __restrict__ resid, long long ld_resid,
                                 float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act, long long ld_act) {
@@ -166,7 +183,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   for (int i = 0; i < 8; ++i) y[i] = 0.f;
   if (valid) {
     const int b = info & ROW_UTT_MASK;
-    const float2 st = __ldg(mr + (long long)b * 8 + c / group_ch);  // group_ch % 8 == 0: one group per thread
+    const float2 st = gn_mean_rstd(stats, bias_gsum, utt, b, c / group_ch);  // group_ch % 8 == 0: one group per thread
     const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
     const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
@@ -216,7 +233,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
 // Saves one pass over the fp32 stream and one launch per stage.
 template <typename T, bool PRECISE, int NCH>
 __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, int M, int group_ch,
-                                   const int* __restrict__ row_info, const float2* __restrict__ mr,
+                                   const int* __restrict__ row_info, const double* __restrict__ stats,
+                                   const double* __restrict__ bias_gsum, const UttTable* __restrict__ utt,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ resid, long long ld_resid, float* __restrict__ out_f32,
                                    long long ld_f32, const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
@@ -237,7 +255,7 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
     const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * ld_resid + c);
     y[i][0] = r.x, y[i][1] = r.y, y[i][2] = r.z, y[i][3] = r.w;
     if (valid) {
-      const float2 st = __ldg(mr + (long long)b * 8 + c / group_ch);
+      const float2 st = gn_mean_rstd(stats, bias_gsum, utt, b, c / group_ch);
       const float4 hv = *reinterpret_cast<const float4*>(h + (long long)row * ld_h + c);
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
       const float x[4] = {hv.x, hv.y, hv.z, hv.w}, ga[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
@@ -332,6 +350,54 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, int
   for (int i = 0; i < MAXV; ++i) {
     int c = lane + 32 * i;
     if (c < C) ActIO<T>::st(orow + c, fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+  }
+}
+
+// Same for C = NCH * 128: a lane owns 4 consecutive channels of every 128-channel chunk, so the row is read with 16-byte
+// loads and written with 8-byte (bf16) / 16-byte (fp32) stores - 3 + 3 memory instructions per lane for C = 384 instead
+// of 12 + 12 scalar ones.
+template <typename T, int NCH>
+__global__ void layernorm_vec_kernel(const float* __restrict__ x, long long ldx, int M, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, T* __restrict__ out, long long ldo) {
+  constexpr int C = NCH * 128;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  if (row >= M) return;
+  float4 v[NCH];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(x + (long long)row * ldx + i * 128 + lane * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+    ss = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, ss))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float o0 = fmaf((v[i].x - mean) * rstd, g.x, be.x), o1 = fmaf((v[i].y - mean) * rstd, g.y, be.y);
+    const float o2 = fmaf((v[i].z - mean) * rstd, g.z, be.z), o3 = fmaf((v[i].w - mean) * rstd, g.w, be.w);
+    T* d = out + (long long)row * ldo + c;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0), u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(d) = u;
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(o0, o1, o2, o3);
+    }
   }
 }
 

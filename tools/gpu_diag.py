@@ -222,7 +222,8 @@ def c_lanes():
 
 
 def c_trace():
-    """Bisect the schedule: compare intermediate buffers (fp32 mode, SIMT kernels, 7 launches per resnet / block)
+    """Bisect the schedule: compare intermediate buffers (fp32 mode, SIMT kernels; the stop indices below were derived for the
+    round-1a schedule of 7 launches per resnet / block and must be re-derived from emit_nfe when the schedule changes)
     against hooks on the dense oracle.  Valid rows per utterance (+ the pad-token row for the residual stream)."""
     import torch
     import matcha_tts_24k_b200 as P
