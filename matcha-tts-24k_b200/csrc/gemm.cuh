@@ -387,7 +387,8 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 template <int MODE, int EPI_LD>
 __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int m0, int n, int lane, int info,
                                           uint32_t valid_mask, uint32_t instat_mask, bool stats_uniform, bool do_stats,
-                                          uint32_t warp_slots, int g_first) {
+                                          uint32_t warp_slots, int g_first, int rb = 0) {
+  // rb > 0: the warp's 32 rows hold exactly two utterances, rows [0, rb) the first and [rb, 32) the second ("split" warp)
   const int rs = lane >> 3, cg = lane & 7;
   const bool col_ok = n < p.N;  // N % 4 == 0: a lane's 4 columns are all inside or all outside
   if (!col_ok) n = 0;           // keep the lane in the shuffles below with harmless addresses, stores predicated off
@@ -398,7 +399,8 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
     ea4 = __ldg(reinterpret_cast<const float4*>(p.ea + n));
     ib4 = __ldg(reinterpret_cast<const float4*>(p.ib + n));
   }
-  float gs = 0.f, gss = 0.f;
+  float gs = 0.f, gss = 0.f, gsB = 0.f, gssB = 0.f;
+  const bool split = rb > 0;
   int cur_utt = -1;
   bf16* oact = reinterpret_cast<bf16*>(p.out_act);
   // All global loads of the block are issued before any store: the residual stream is updated in place, so the compiler
@@ -419,7 +421,7 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
     const float4 a = ptx::lds128(stg + (r * EPI_LD + cg * 4) * 4);
     int info_r = 0;
     if constexpr (MODE == EPI_STATS) {
-      if (do_stats && !stats_uniform) info_r = __shfl_sync(0xffffffffu, info, r);  // utterance id per row: boundary warps only
+      if (do_stats && !stats_uniform && !split) info_r = __shfl_sync(0xffffffffu, info, r);  // utterance id per row: multi-boundary warps only
     }
     if (m >= p.M || !col_ok) continue;
     float x0 = a.x + b4.x, x1 = a.y + b4.y, x2 = a.z + b4.z, x3 = a.w + b4.w;
@@ -428,9 +430,16 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
       *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
     } else if constexpr (MODE == EPI_STATS) {
       *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
-      if (do_stats && ((instat_mask >> r) & 1u)) {
-        // Rows are sorted by utterance, so a lane sees a non-decreasing utterance id; in a warp that straddles a segment
-        // boundary the running sums are flushed whenever the id changes (and once at the end), otherwise never here.
+      if (do_stats && (stats_uniform || split)) {
+        // one utterance (or two, split at row rb): branch-free accumulation into the first / second set
+        const bool in = ((instat_mask >> r) & 1u) != 0;
+        const float s4 = in ? (x0 + x1) + (x2 + x3) : 0.f;
+        const float q4 = in ? fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3) : 0.f;
+        if (!split || r < rb) gs += s4, gss += q4;
+        else gsB += s4, gssB += q4;
+      } else if (do_stats && ((instat_mask >> r) & 1u)) {
+        // Three or more utterances inside 32 rows (very short utterances).  Rows are sorted by utterance, so a lane sees a
+        // non-decreasing utterance id; the running sums are flushed whenever the id changes (and once at the end).
         const int ur = stats_uniform ? 0 : (info_r & ROW_UTT_MASK);
         if (ur != cur_utt) {
           if (cur_utt >= 0 && !stats_uniform) {
@@ -479,18 +488,41 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
     }
   }
   if constexpr (MODE == EPI_STATS) {
-    if (do_stats && !stats_uniform && cur_utt >= 0 && col_ok) {  // boundary warp: each lane flushes its last segment
+    if (do_stats && !stats_uniform && !split && cur_utt >= 0 && col_ok) {  // multi-boundary warp: each lane flushes its last segment
       const long long o = ((long long)cur_utt * 8 + n / p.group_ch) * 2;
       atomicAdd(p.stats + o, (double)gs);
       atomicAdd(p.stats + o + 1, (double)gss);
     }
-    if (do_stats && stats_uniform) {  // reduce over the 4 row phases, then one atomic pair per 4-column group
+    // Sums of one utterance -> global: combine the column quads of a GroupNorm group first (segmented scan over cg), then
+    // only the segment tails issue fp64 atomics (same-address atomics serialise in L2, ~30 cycles each).
+    auto flush_global = [&](float s_, float ss_, int utt_) {
+      s_ += __shfl_xor_sync(0xffffffffu, s_, 8), ss_ += __shfl_xor_sync(0xffffffffu, ss_, 8);
+      s_ += __shfl_xor_sync(0xffffffffu, s_, 16), ss_ += __shfl_xor_sync(0xffffffffu, ss_, 16);
+      const int gid = col_ok ? n / p.group_ch : 64 + cg;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const float us = __shfl_up_sync(0xffffffffu, s_, o, 8), uss = __shfl_up_sync(0xffffffffu, ss_, o, 8);
+        const int ug = __shfl_up_sync(0xffffffffu, gid, o, 8);
+        if (cg >= o && ug == gid) s_ += us, ss_ += uss;
+      }
+      const int ng = __shfl_down_sync(0xffffffffu, gid, 1, 8);
+      if (rs == 0 && col_ok && (cg == 7 || ng != gid) && (s_ != 0.f || ss_ != 0.f)) {
+        const long long o = ((long long)utt_ * 8 + gid) * 2;
+        atomicAdd(p.stats + o, (double)s_);
+        atomicAdd(p.stats + o + 1, (double)ss_);
+      }
+    };
+    if (do_stats && split) {
+      flush_global(gs, gss, __shfl_sync(0xffffffffu, info, 0) & ROW_UTT_MASK);
+      flush_global(gsB, gssB, __shfl_sync(0xffffffffu, info, 31) & ROW_UTT_MASK);
+    }
+    if (do_stats && stats_uniform && !warp_slots) flush_global(gs, gss, __shfl_sync(0xffffffffu, info, 0) & ROW_UTT_MASK);
+    if (do_stats && stats_uniform && warp_slots) {  // reduce over the 4 row phases, then this warp's smem slots
       gs += __shfl_xor_sync(0xffffffffu, gs, 8);
       gss += __shfl_xor_sync(0xffffffffu, gss, 8);
       gs += __shfl_xor_sync(0xffffffffu, gs, 16);
       gss += __shfl_xor_sync(0xffffffffu, gss, 16);
-      const int utt = __shfl_sync(0xffffffffu, info, 0) & ROW_UTT_MASK;
-      if (warp_slots) {
+      {
         // The whole tile is one utterance: combine the 8 column groups of this block that fall into the same GroupNorm
         // group (segmented scan over cg), then the segment tails add into this warp's private smem slots.  No atomics,
         // fixed order -> bitwise reproducible; the last warp of the tile reduces the 8 warps' slots (gemm_tc_kernel).
@@ -507,10 +539,6 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
           ptx::sts32(a, ptx::lds32(a) + gs);
           ptx::sts32(a + 4, ptx::lds32(a + 4) + gss);
         }
-      } else if (rs == 0 && col_ok && (gs != 0.f || gss != 0.f)) {
-        const long long o = ((long long)utt * 8 + n / p.group_ch) * 2;
-        atomicAdd(p.stats + o, (double)gs);
-        atomicAdd(p.stats + o + 1, (double)gss);
       }
     }
   }
@@ -577,12 +605,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
   const uint32_t instat_mask = __ballot_sync(0xffffffffu, (info & ROW_INSTAT) != 0);
   bool do_stats = false, uniform = false;
   uint32_t warp_slots = 0;
-  int tile_utt = 0, g_first = 0;
+  int tile_utt = 0, g_first = 0, rb = 0;
   if constexpr (MODE == EPI_STATS) {
     do_stats = p.fused_stats != 0;
     const int utt = info & ROW_UTT_MASK;
     if (do_stats) {
-      uniform = __all_sync(0xffffffffu, utt == __shfl_sync(0xffffffffu, utt, 0));
+      const int utt_first = __shfl_sync(0xffffffffu, utt, 0), utt_last = __shfl_sync(0xffffffffu, utt, 31);
+      uniform = __all_sync(0xffffffffu, utt == utt_first);
+      // exactly two utterances in the warp (rows are sorted by utterance): split row = number of rows of the first one.
+      // Rows past M carry utterance 0 in `info`; such a warp takes the generic multi-boundary path.
+      if (!uniform && __all_sync(0xffffffffu, utt == utt_first || utt == utt_last) && m0 + 31 < p.M)
+        rb = __popc(__ballot_sync(0xffffffffu, utt == utt_first));
       // If the 128 rows of the tile are one utterance (the common case) the sums are gathered per CTA in smem.
       const int mt = m0 - q * 32;
       const int u_lo = __ldg(p.row_info + min(mt, p.M - 1)) & ROW_UTT_MASK;
@@ -591,6 +624,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         warp_slots = gn_slots + ((acc * 8 + ewarp) * 16) * 4;
         tile_utt = u_lo, g_first = n0 / p.group_ch;
         uniform = true;  // rows past M carry no ROW_INSTAT flag and add nothing
+        rb = 0;
       }
     }
   }
@@ -620,9 +654,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     __syncwarp();
     if constexpr (WIDE) {
       if (wide) epi_block_wide<MODE, EPI_LD>(p, stg, m0, n0 + c, lane, valid_mask);
-      else epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first);
+      else epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first, rb);
     } else {
-      epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first);
+      epi_block<MODE, EPI_LD>(p, stg, m0, n0 + c + (lane & 7) * 4, lane, info, valid_mask, instat_mask, uniform, do_stats, warp_slots, g_first, rb);
     }
     __syncwarp();
   }
