@@ -176,7 +176,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   const int m = (int)(idx / c8);
   if (m >= M) return;
   const int c = (int)(idx % c8) * 8;
+  // every load that does not depend on the row flags is issued up front: one memory round trip instead of three
   const int info = __ldg(row_info + m);
+  const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
+  const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  if (resid) {
+    r0 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
+    r1 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c + 4);
+  }
   const bool valid = (info & ROW_VALID) != 0;
   float y[8];
 #pragma unroll
@@ -184,8 +192,6 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   if (valid) {
     const int b = info & ROW_UTT_MASK;
     const float2 st = gn_mean_rstd(stats, bias_gsum, utt, b, c / group_ch);  // group_ch % 8 == 0: one group per thread
-    const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
-    const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
     const float x[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -202,8 +208,6 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
     }
   }
   if (resid) {
-    const float4 r0 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
-    const float4 r1 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c + 4);
     y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w, y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
   }
   if (out_f32) {
@@ -254,9 +258,9 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
     const int c = i * 128 + lane * 4;
     const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * ld_resid + c);
     y[i][0] = r.x, y[i][1] = r.y, y[i][2] = r.z, y[i][3] = r.w;
+    const float4 hv = *reinterpret_cast<const float4*>(h + (long long)row * ld_h + c);  // unconditional: overlaps the flag load
     if (valid) {
       const float2 st = gn_mean_rstd(stats, bias_gsum, utt, b, c / group_ch);
-      const float4 hv = *reinterpret_cast<const float4*>(h + (long long)row * ld_h + c);
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
       const float x[4] = {hv.x, hv.y, hv.z, hv.w}, ga[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll

@@ -187,6 +187,42 @@ def c_epimodes():
               f"finite={bool(torch.isfinite(out).all())}", flush=True)
 
 
+def c_steptime():
+    """Time of individual launches of the first estimator stage on cfg2 (direct launches): t(stop_after=k) - t(stop_after=k-1).
+    Schedule: 1 memset, 2 conv1+stats, 3 res_conv, 4 gn_apply, 5 conv2+stats, 6 gn_apply+LN, 7 QKV, 8 attention, 9 out-proj,
+    10 LN, 11 FF1+snake, 12 FF2."""
+    import types
+    import torch
+    import matcha_tts_24k_b200 as P
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16", flags=1).eval().cuda()
+    P.synthetic.fill_named_seed(m.estimator, 1234)
+    lengths = P.synthetic.config_lengths(os.environ.get("DIAG_WORKLOAD", "cfg2"))
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
+    t = torch.tensor(0.3)
+    m.estimator(z, mask, mu, t)
+    torch.cuda.synchronize()
+    names = {1: "memset", 2: "conv1+stats", 3: "res_conv", 4: "gn_apply", 5: "conv2+stats", 6: "gn_apply+LN", 7: "QKV", 8: "attention",
+             9: "out-proj", 10: "LN", 11: "FF1+snake", 12: "FF2"}
+    prev = None
+    for k in range(0, 13):
+        m._lib.cfm_debug_stop_after(m._handle, k)
+        for _ in range(3):
+            m.estimator(z, mask, mu, t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            m.estimator(z, mask, mu, t)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 10 * 1e3
+        if prev is not None:
+            print(f"[steptime {k:2d} {names.get(k, '?'):12s}] {us - prev:7.1f} us", flush=True)
+        prev = us
+    m._lib.cfm_debug_stop_after(m._handle, -1)
+
+
 def c_lanes():
     """Decode time of cfg2 / cfg3 / cfg4 against the number of lanes (parallel graph branches)."""
     import types
