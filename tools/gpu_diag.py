@@ -170,9 +170,11 @@ def c_epimodes():
     ts = torch.linspace(0, 1, 11, device="cuda")
     combos = os.environ.get("DIAG_COMBOS", "0:1,1:1,4:1,8:1,16:1,63:1,63:2,0:2,0:0")
     for item in combos.split(","):
-        tma, pair = (int(v) for v in item.split(":"))
+        f = [int(v) for v in item.split(":")]
+        tma, pair = f[0], f[1]
         m.set_option("tma_epi", tma)
         m.set_option("pair_mode", pair)
+        m.set_option("pdl", f[2] if len(f) > 2 else 0)
         for _ in range(2):
             out = m.solve(z, ts, mu, mask, lengths=lengths)
         torch.cuda.synchronize()
@@ -183,7 +185,7 @@ def c_epimodes():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(f"[epimodes tma_mask={tma} pair_mode={pair}] {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s "
+        print(f"[epimodes tma_mask={tma} pair_mode={pair} pdl={f[2] if len(f) > 2 else 0}] {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s "
               f"finite={bool(torch.isfinite(out).all())}", flush=True)
 
 
