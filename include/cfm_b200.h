@@ -100,7 +100,8 @@ int cfm_set_speakers(cfm_handle* h, const float* spks);
 int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
 
 /* Kernel-selection switches for A/B measurements (take effect at the next cfm_plan / debug GEMM): "tma_epi" 0/1 (TMA-store
- * GEMM epilogue), "pair_mode" 0/1/2 (CTA-pair GEMM never / where it measures faster / always), "pdl" 0/1, "cluster" 1/2/4.
+ * GEMM epilogue), "pair_mode" 0/1/2 (CTA-pair GEMM never / where it measures faster / always), "pdl" -1/0/1 (programmatic dependent launch: auto = small plans only / off /
+ * on), "cluster" 1/2/4, "small_tiles" M (GEMMs of at most M rows use 64-column tiles; 0 = never).
  * Results stay within the precision mode's tolerance for every setting. */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
 

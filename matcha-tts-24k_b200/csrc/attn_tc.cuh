@@ -83,7 +83,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   const int4 w = work[blockIdx.x];  // plan-constant tables: safe to read before pdl_wait
   const UttTable u = utt[w.x];
   const int head = w.y, q0 = w.z;
@@ -103,6 +102,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       ptx::mbar_init(bar_pv + i, 1);
     }
     ptx::fence_mbar_init();
+    // Q and the first two K / V tiles are requested right away: their L2 latency overlaps the TMEM allocation and the
+    // CTA-wide barrier below instead of following them (the barriers they complete on are initialised and fenced above).
+    ptx::pdl_wait();
+    ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+    ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_q, bar_q, head * Cfg::D, row0 + q0);
+    for (int j = 0; j < 2 && j < n_tiles; ++j) {
+      ptx::mbar_expect_tx(bar_k + j, Cfg::K_BYTES);
+      ptx::tma_load_2d(smem + Cfg::OFF_K + j * Cfg::K_BYTES, &tm_kv, bar_k + j, inner + head * Cfg::D, row0 + j * Cfg::KT);
+      ptx::mbar_expect_tx(bar_v + j, Cfg::V_BYTES);
+      ptx::tma_load_2d(smem + Cfg::OFF_V + j * Cfg::V_BYTES, &tm_kv, bar_v + j, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+    }
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -120,16 +130,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   //   softmax     : wait S_j -> max -> P_j = exp2(...) -> smem P[b] -> O += PV_{j-1} (finished long ago), O *= corr -> arrive P_j
   // so the softmax warps never wait on an MMA issued in the same iteration.
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
-      ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_q, bar_q, head * Cfg::D, row0 + q0);
-      for (int j = 0; j < n_tiles; ++j) {
+    if (lane == 0) {  // ---------------- TMA producer (tiles 0 and 1 were requested in the prologue)
+      for (int j = 2; j < n_tiles; ++j) {
         const int b = j & 1;
         const uint32_t prev = ((j >> 1) - 1) & 1;  // parity of the previous use of buffer b
-        if (j >= 2) ptx::mbar_wait(bar_s + b, prev);  // S_{j-2} complete: K[b] free
+        ptx::mbar_wait(bar_s + b, prev);  // S_{j-2} complete: K[b] free
         ptx::mbar_expect_tx(bar_k + b, Cfg::K_BYTES);
         ptx::tma_load_2d(smem + Cfg::OFF_K + b * Cfg::K_BYTES, &tm_kv, bar_k + b, inner + head * Cfg::D, row0 + j * Cfg::KT);
-        if (j >= 2) ptx::mbar_wait(bar_pv + b, prev);  // PV_{j-2} complete: V[b] free
+        ptx::mbar_wait(bar_pv + b, prev);  // PV_{j-2} complete: V[b] free
         ptx::mbar_expect_tx(bar_v + b, Cfg::V_BYTES);
         ptx::tma_load_2d(smem + Cfg::OFF_V + b * Cfg::V_BYTES, &tm_kv, bar_v + b, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
       }
@@ -168,6 +176,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         ptx::umma_commit(bar_pv + b);
         if (j + 2 < n_tiles) issue_s(j + 2);
       }
+      ptx::pdl_launch_dependents();  // last MMA issued: the next kernel's launch overlaps this CTA's final softmax pass and epilogue
       if (do_prof) {
         prof[0] = (unsigned long long)(clock64() - t_start), prof[1] = wq, prof[2] = wk, prof[3] = wp, prof[4] = wv;
         prof[5] = (unsigned long long)n_tiles;

@@ -124,8 +124,11 @@ struct cfm_handle {
   int sm_count = 148;
   int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
   int cluster = 1;                              // 1-CTA kernel: CTAs sharing one weight tile via TMA multicast (no gain measured)
-  int pdl = 0;                                  // programmatic dependent launch between the kernels of a decode (CFM_B200_PDL=1);
-                                                // measured neutral on cfg1/cfg2, so off by default
+  int pdl = -1;                                 // programmatic dependent launch between the kernels of a decode: -1 auto (on for
+                                                // plans of <= 2048 packed rows: -8 % on cfg1, where launch latency dominates; off
+                                                // above: +0.5-2 % on cfg2 / cfg4), 0 off, 1 on (CFM_B200_PDL, cfm_set_option "pdl")
+  int pdl_now = 0;                              // resolved per plan
+  int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   int tma_epi = 1 << EPI_RESID;                 // bit m: TMA-store epilogue for EpiMode m.  Measured on cfg2: the in-place
                                                 // residual add through cp.reduce.async.bulk saves 1.2 ms per decode; STORE / SNAKE /
@@ -398,6 +401,13 @@ int make_out_tmap(cfm_handle* h, CUtensorMap* tm, const void* base, bool f32, lo
   return 0;
 }
 
+// Small batches (the server's B = 1 requests) leave most SMs idle and every kernel is latency-bound: narrow tiles spread a
+// GEMM over 3-4x more CTAs and shorten each CTA's epilogue (cfg1: measured in DESIGN.md section 7).
+int pick_bn_small(int N) {
+  if (N % 64 == 0) return 64;
+  return N <= 64 ? 64 : 128;
+}
+
 int pick_bn(int N) {
   if (N % 256 == 0) return 256;
   if (N % 192 == 0) return 192;
@@ -423,7 +433,7 @@ int launch_ex(cfm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (h->pdl) {
+  if (h->pdl_now) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -495,7 +505,7 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     return 0;
   }
   if (p.K % 64 != 0) return fail(h, CFM_ERR_INVALID, "tensor-core GEMM needs K %% 64 == 0 (K=%d)", p.K);
-  const int bn = pick_bn(p.N);
+  const int bn = (h->small_tiles && p.M <= h->small_tiles) ? pick_bn_small(p.N) : pick_bn(p.N);
   CUtensorMap tmA[2], tmW;
   for (int i = 0; i < 2; ++i) {
     const int src = p.A[i] ? i : 0;
@@ -682,7 +692,7 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
   const int I = h->inner(), D = h->cfg.head_dim;
   const float scale = 1.0f / sqrtf((float)D);
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
-  if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl != 0);
+  if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl_now != 0);
   if (h->bf) {
     if (D == 64)
       attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
@@ -1019,7 +1029,7 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h->bf = cfg->precision == CFM_PREC_BF16;
   h->es = h->bf ? 2 : 4;
   h->sm_count = prop.multiProcessorCount;
-  if (const char* e = getenv("CFM_B200_PDL")) h->pdl = atoi(e) != 0;
+  if (const char* e = getenv("CFM_B200_PDL")) h->pdl = atoi(e) < 0 ? -1 : atoi(e) != 0;
   if (const char* e = getenv("CFM_B200_PAIR")) h->pair_mode = atoi(e);  // 0 never, 1 long-K GEMMs (default), 2 always
   if (const char* e = getenv("CFM_B200_TMA_EPI")) h->tma_epi = atoi(e);
   if (const char* e = getenv("CFM_B200_LANES")) h->lanes_req = std::max(1, std::min(16, atoi(e)));
@@ -1161,6 +1171,7 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     s2 += L2 + 2;
   }
   pl->M2 = s2, pl->M1 = 2 * s2;
+  h->pdl_now = h->pdl < 0 ? (pl->M1 <= 2048 ? 1 : 0) : h->pdl;
   std::vector<int> i1(pl->M1, 0), i2(pl->M2, 0);
   std::vector<int4> w1, w2;
   std::vector<int> wfirst1(batch + 1, 0), wfirst2(batch + 1, 0);
@@ -1439,7 +1450,8 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   if (!h || !key) return fail(h, CFM_ERR_INVALID, "null argument");
   if (strcmp(key, "tma_epi") == 0) h->tma_epi = value == 1 ? 0x3f : value;
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
-  else if (strcmp(key, "pdl") == 0) h->pdl = value != 0;
+  else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
+  else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
   else return fail(h, CFM_ERR_INVALID, "unknown option '%s' or value %d out of range", key, (int)value);
   return 0;

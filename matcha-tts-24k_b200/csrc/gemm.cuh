@@ -848,7 +848,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   // Cluster of CL CTAs = CL consecutive m-tiles of one n-tile ("super-tile"); every CTA of a cluster walks the same
   // super-tile list in lock step (a CTA whose m-tile lies past M still runs: its loads are zero-filled, stores predicated).
   const int CL = p.cluster;
@@ -959,6 +958,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ptx::umma_commit(&tfull_bar[acc]);
       }
       if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
+      // Programmatic dependent launch: the next kernel may be scheduled once every CTA has issued its last MMA, so its launch
+      // latency and prologue overlap this kernel's last epilogue instead of its whole run (an early trigger lets the
+      // dependent CTAs sit on SMs that this grid's later tiles still need).
+      ptx::pdl_launch_dependents();
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps: TMEM -> registers -> smem transpose -> coalesced global I/O ============
@@ -1065,7 +1068,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   const int rank = (int)ptx::cluster_ctarank();  // 0 = leader
   const int m_pairs = (p.M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -1165,6 +1167,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
     }
+    if (lane == 0) ptx::pdl_launch_dependents();  // leader: after its last MMA; follower: nothing left to issue
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
     const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * Cfg::EPI_WARP_BYTES;

@@ -147,7 +147,6 @@ __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M
 // PADDED length).
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, const double* __restrict__ bias_gsum,
                                    const UttTable* __restrict__ utt, int n_utt, int group_ch, float2* __restrict__ mr) {
-  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_utt * 8) return;
@@ -169,7 +168,6 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ addvec, const float* __restrict__ resid, long long ld_resid,
                                 float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act, long long ld_act) {
-  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = C >> 3;
@@ -210,6 +208,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   if (resid) {
     y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w, y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
   }
+  ptx::pdl_launch_dependents();  // inputs consumed: the dependent kernel's launch overlaps the stores of the last wave
   if (out_f32) {
     *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c) = make_float4(y[0], y[1], y[2], y[3]);
     *reinterpret_cast<float4*>(out_f32 + (long long)m * ld_f32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -245,7 +244,6 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
                                    T* __restrict__ out_ln, long long ld_ln) {
   constexpr int C = NCH * 128;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (row >= M) return;
   const int info = __ldg(row_info + row);
@@ -286,6 +284,7 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+  ptx::pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = i * 128 + lane * 4;
@@ -324,7 +323,6 @@ template <typename T, int MAXV>
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, T* __restrict__ out, long long ldo) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (warp >= M) return;
   const float* xr = x + (long long)warp * ldx;
@@ -349,6 +347,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, int
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+  ptx::pdl_launch_dependents();
   T* orow = out + (long long)warp * ldo;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -365,7 +364,6 @@ __global__ void layernorm_vec_kernel(const float* __restrict__ x, long long ldx,
                                      const float* __restrict__ beta, T* __restrict__ out, long long ldo) {
   constexpr int C = NCH * 128;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (row >= M) return;
   float4 v[NCH];
@@ -387,6 +385,7 @@ __global__ void layernorm_vec_kernel(const float* __restrict__ x, long long ldx,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / (float)C + 1e-5f);
+  ptx::pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = i * 128 + lane * 4;
