@@ -164,8 +164,23 @@ class CFM(torch.nn.Module):
         if temperature != 1.0:
             noise = noise * temperature
         z = mu + noise if self.use_mu_prior else noise
-        t_span = torch.linspace(0, 1, n_timesteps + 1, device=mu.device)
-        return self.solve(z, t_span=t_span, mu=mu, mask=mask, lengths=lengths, spks=spks)
+        return self.solve(z, t_span=self._t_span(int(n_timesteps), mu.device), mu=mu, mask=mask, lengths=lengths, spks=spks)
+
+    def _t_span(self, n_timesteps: int, device):
+        """linspace(0, 1, n + 1) evaluated on the caller's device as the reference does (flow_matching.py:57) and cached with
+        its host copy, so that a repeated forward() does not pay a device-to-host sync for the time grid."""
+        cache = self.__dict__.setdefault("_tspan_cache", {})
+        key = (n_timesteps, str(device))
+        if key not in cache:
+            t = torch.linspace(0, 1, n_timesteps + 1, device=device)
+            cache[key] = (t, [float(v) for v in t.to(torch.float32).cpu().tolist()])
+        return cache[key][0]
+
+    def _t_list(self, t_span):
+        for t, lst in self.__dict__.get("_tspan_cache", {}).values():
+            if t is t_span:
+                return lst
+        return [float(v) for v in t_span.detach().to(torch.float32).cpu().tolist()]
 
     @torch.inference_mode()
     def solve(self, x, t_span, mu, mask, lengths=None, spks=None):
@@ -185,7 +200,7 @@ class CFM(torch.nn.Module):
             raise ValueError("x, mu and mask disagree on (B, F, T)")
         if lengths is None:
             lengths = lengths_from_mask(mask)
-        ts = [float(v) for v in t_span.detach().to(torch.float32).cpu().tolist()]
+        ts = self._t_list(t_span)
         lib, handle = self._ensure(mu_.device, [int(v) for v in lengths], T, ts, self.solver)
         out = torch.empty_like(mu_)
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
