@@ -75,8 +75,8 @@ int cfm_load_weights(cfm_handle* h, const cfm_weight_desc* descs, int32_t n);
 /* Prepares a decode of `batch` utterances padded to `t_pad` frames (t_pad even, reference
  * matcha/utils/model.py:15-21) with valid lengths `lengths[b]` (prefix masks, reference
  * matcha/utils/model.py:7-9) over the time grid `t_span[0..n_points)` with a torchdiffeq fixed-grid solver
- * (call site flow_matching.py:60-63).  Builds the packed row tables, workspace and the CUDA graph of the
- * whole ODE loop.  Replaces the per-call setup of BASECFM.solve + OdeSolverWrapper. */
+ * (call site flow_matching.py:60-63).  Builds the packed row tables and the workspace; the CUDA graph of the
+ * whole ODE loop is captured when the plan is reused (option "graph_after").  Replaces the per-call setup of BASECFM.solve + OdeSolverWrapper. */
 int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad, const float* t_span, int32_t n_points,
              int32_t solver);
 
@@ -101,7 +101,8 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
 
 /* Kernel-selection switches for A/B measurements (take effect at the next cfm_plan / debug GEMM): "tma_epi" 0/1 (TMA-store
  * GEMM epilogue), "pair_mode" 0/1/2 (CTA-pair GEMM never / where it measures faster / always), "pdl" -1/0/1 (programmatic dependent launch: auto = small plans only / off /
- * on), "cluster" 1/2/4, "small_tiles" M (GEMMs of at most M rows use 64-column tiles; 0 = never).
+ * on), "cluster" 1/2/4, "small_tiles" M (GEMMs of at most M rows use 64-column tiles; 0 = never), "graph_after" n (a plan's first n decodes use
+ * direct launches, its CUDA graph is captured before decode n + 1; 0 = capture inside cfm_plan; default 1).
  * Results stay within the precision mode's tolerance for every setting. */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
 

@@ -107,6 +107,7 @@ struct Plan {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   long long launches_per_solve = 0;
+  int solves = 0;  // decodes run with this plan (the graph is captured lazily, see cfm_plan)
 };
 
 }  // namespace
@@ -128,6 +129,8 @@ struct cfm_handle {
                                                 // plans of <= 2048 packed rows: -8 % on cfg1, where launch latency dominates; off
                                                 // above: +0.5-2 % on cfg2 / cfg4), 0 off, 1 on (CFM_B200_PDL, cfm_set_option "pdl")
   int pdl_now = 0;                              // resolved per plan
+  int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
+                                                // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   int tma_epi = 1 << EPI_RESID;                 // bit m: TMA-store epilogue for EpiMode m.  Measured on cfg2: the in-place
@@ -995,6 +998,21 @@ int build_stages(cfm_handle* h, Plan* pl, const float* t_span, int n_points, int
   return 0;
 }
 
+int capture_graph(cfm_handle* h, Plan* pl) {
+  if (h->cfg.flags & CFM_FLAG_NO_GRAPH) return 0;
+  const long long saved = h->launch_counter;
+  h->launch_counter = 0;
+  CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+  int r = emit_ode_loop(h, pl, h->own_stream);
+  cudaError_t e = cudaStreamEndCapture(h->own_stream, &pl->graph);
+  if (r) return r;
+  if (e != cudaSuccess) return fail(h, CFM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  CK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+  pl->launches_per_solve = h->launch_counter + 3;  // + pack x, pack mu, unpack
+  h->launch_counter = saved;
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -1292,17 +1310,12 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   }
   CK(cudaDeviceSynchronize());
 
-  // ---- capture the whole ODE loop as one CUDA graph
+  // ---- the whole ODE loop as one CUDA graph: captured here, or lazily before the plan's (graph_after + 1)-th decode.
+  // Capturing and instantiating ~1200 nodes costs more than a B = 1 decode itself, and a server sees a new length with
+  // almost every request, so a plan's first decode uses direct launches and the graph is built only when the plan is reused.
   h->launch_counter = 0;
-  if (!(h->cfg.flags & CFM_FLAG_NO_GRAPH)) {
-    CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-    int r = emit_ode_loop(h, pl, h->own_stream);
-    cudaError_t e = cudaStreamEndCapture(h->own_stream, &pl->graph);
-    if (r) return r;
-    if (e != cudaSuccess) return fail(h, CFM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    CK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
-    pl->launches_per_solve = h->launch_counter + 3;  // + pack x, pack mu, unpack
-  }
+  pl->solves = 0;
+  if (h->graph_after == 0) CKR(capture_graph(h, pl));
   return 0;
 }
 
@@ -1313,6 +1326,8 @@ int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(h->cfg.device));
   h->launch_counter = 0;
+  if (!pl->exec && pl->solves >= h->graph_after) CKR(capture_graph(h, pl));
+  pl->solves++;
   CKR(emit_pack(h, pl, z, mu, s));
   if (pl->exec) {
     CK(cudaGraphLaunch(pl->exec, s));
@@ -1451,6 +1466,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   if (strcmp(key, "tma_epi") == 0) h->tma_epi = value == 1 ? 0x3f : value;
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
+  else if (strcmp(key, "graph_after") == 0 && value >= 0) h->graph_after = value;
   else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
   else return fail(h, CFM_ERR_INVALID, "unknown option '%s' or value %d out of range", key, (int)value);

@@ -567,7 +567,17 @@ def c_plantime():
         torch.cuda.synchronize(); t0 = _t.perf_counter()
         out = m.solve(z, ts, mu, mask, lengths=lengths); torch.cuda.synchronize(); t1 = _t.perf_counter()
         out = m.solve(z, ts, mu, mask, lengths=lengths); torch.cuda.synchronize(); t2 = _t.perf_counter()
-        print(f"[plantime] {name}: first call (plan + capture + decode) {(t1 - t0) * 1e3:.1f} ms, second call {(t2 - t1) * 1e3:.1f} ms, {m.plan_info()}")
+        out = m.solve(z, ts, mu, mask, lengths=lengths); torch.cuda.synchronize(); t3 = _t.perf_counter()
+        print(f"[plantime] {name}: first call (plan + direct-launch decode) {(t1 - t0) * 1e3:.1f} ms, second call (graph capture + decode) "
+              f"{(t2 - t1) * 1e3:.1f} ms, third call (graph replay) {(t3 - t2) * 1e3:.1f} ms, {m.plan_info()}")
+        for k, ga in enumerate((0, 1, 0, 1)):  # a NEW shape per call (what a server sees), both graph policies, warm library
+            m.set_option("graph_after", ga)
+            lengths2 = [max(1, v - 2 * (k + 1)) for v in lengths]
+            mu2, mask2, z2, _ = P.synthetic.make_inputs(lengths2, seed=1, device="cuda")
+            torch.cuda.synchronize(); t0 = _t.perf_counter()
+            out = m.solve(z2, ts, mu2, mask2, lengths=lengths2); torch.cuda.synchronize(); t1 = _t.perf_counter()
+            print(f"[plantime] {name} new shape, graph_after={ga}: plan + first decode {(t1 - t0) * 1e3:.1f} ms")
+        m.set_option("graph_after", 1)
 
 
 CHECKS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("c_")}
