@@ -234,6 +234,25 @@ def test_kernel_selection_switches_keep_parity(tma_mask, pair_mode):
         m.set_option("no_such_switch", 1)
 
 
+def test_small_batch_path_switches_keep_parity_and_graph_is_lazy():
+    """The server-side path (B = 1): 64-column GEMM tiles for M <= small_tiles, programmatic dependent launch, and the CUDA
+    graph captured only when a plan is reused.  Every combination stays within the bf16 tolerance of the oracle, and the
+    direct-launch first decode of a plan equals its graph replays."""
+    ora, m = pair(syn.PROD, "midpoint", "bf16")
+    mu, mask, z, _ = syn.make_inputs([150], seed=8)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    m.refresh(torch.device("cuda", torch.cuda.current_device()))
+    for small, pdl, graph_after in ((1024, 1, 1), (0, 0, 0), (1024, 0, 2), (0, 1, 1)):
+        m.set_option("small_tiles", small)
+        m.set_option("pdl", pdl)
+        m.set_option("graph_after", graph_after)
+        outs = [m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda()).cpu() for _ in range(4)]
+        check(outs[0], ref, "bf16", f"B=1 small_tiles={small} pdl={pdl} graph_after={graph_after}")
+        for o in outs[1:]:
+            assert rel_l2(o, outs[0]) < 1e-6
+
+
 @pytest.mark.parametrize("lanes", [2, 3, 5])
 def test_lanes_are_invisible_in_the_result(lanes):
     """cfm_set_lanes: the batch is cut into utterance groups that run as parallel graph branches.  Against the oracle
