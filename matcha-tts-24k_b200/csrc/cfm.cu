@@ -129,6 +129,7 @@ struct cfm_handle {
                                                 // plans of <= 2048 packed rows: -8 % on cfg1, where launch latency dominates; off
                                                 // above: +0.5-2 % on cfg2 / cfg4), 0 off, 1 on (CFM_B200_PDL, cfm_set_option "pdl")
   int pdl_now = 0;                              // resolved per plan
+  int direct_epi = 0;                           // bit m: direct (256-bit store, no smem) epilogue for bf16-output EpiMode m; "direct_epi"
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
@@ -519,6 +520,8 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   const bool bf_mode = p.mode == EPI_STORE || p.mode == EPI_SNAKE || p.mode == EPI_MASK;
   const bool red_mode = p.mode == EPI_RESID && p.out_act == nullptr && p.resid != nullptr && p.resid == p.out_f32 && p.ld_resid == p.ld_f32;
   p.tma_epi = (((h->tma_epi >> p.mode) & 1) && (bf_mode || red_mode) && p.N % 8 == 0 && bn % 32 == 0) ? 1 : 0;
+  p.direct_epi = (((h->direct_epi >> p.mode) & 1) && bf_mode && !p.tma_epi && p.N % 32 == 0 && p.ld_act % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.out_act) & 31) == 0) ? 1 : 0;
   CUtensorMap tmO = tmA[0];
   if (p.tma_epi) {
     if (red_mode) CKR(make_out_tmap(h, &tmO, p.out_f32, true, p.N, p.M, p.ld_f32));
@@ -1467,6 +1470,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
   else if (strcmp(key, "graph_after") == 0 && value >= 0) h->graph_after = value;
+  else if (strcmp(key, "direct_epi") == 0 && value >= 0) h->direct_epi = value;
   else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
   else return fail(h, CFM_ERR_INVALID, "unknown option '%s' or value %d out of range", key, (int)value);

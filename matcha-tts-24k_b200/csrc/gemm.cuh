@@ -75,6 +75,7 @@ struct GemmParams {
   long long ld_k;
   int cluster;  // CTAs per cluster sharing one weight tile via TMA multicast (1, 2 or 4)
   int pair;     // 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 per pair)
+  int direct_epi;  // 1: epilogue_tile_direct (bf16 modes: rows stored straight from registers with 256-bit stores, no smem)
   int tma_epi;  // 1: epilogue_tile_tma (row-per-thread math, swizzled smem staging, TMA store / reduce-add); see launch_gemm
   unsigned long long* prof;  // debug: CTA 0 writes per-role cycle counters (see gemm_tc_kernel); nullptr = off
 };
@@ -800,6 +801,86 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 }
 
 // ------------------------------------------------------------------------------------------------
+// Direct epilogue (bf16-output modes): no shared-memory staging at all.  tcgen05.ld leaves each thread one accumulator row;
+// 32 consecutive bf16 columns of it are exactly two 32-byte sectors, written with two 256-bit stores (st.global.v8.b32).  A warp
+// instruction therefore touches 32 different rows, but every sector is written whole and nothing goes through the shared
+// memory port that TMA writes, UMMA operand reads and the transposing epilogue's ld/st.shared compete for (ncu: the staging
+// ld.shared take 2x their ideal wavefronts inside these kernels).  Requires N % 32 == 0, ld_act % 16 == 0, 32-byte aligned base.
+__device__ __forceinline__ void stg256(void* dst, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+template <int BN, int MODE, typename Release>
+__device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32_t taddr, int m0, int n0, int half, int lane,
+                                                     Release&& release) {
+  constexpr int UNITS = BN / 32;
+  const int m = m0 + lane;
+  bool valid = true;
+  if constexpr (MODE == EPI_MASK) valid = (load_row_info(p, m) & ROW_VALID) != 0;
+  bf16* orow = reinterpret_cast<bf16*>(p.out_act) + (long long)m * p.ld_act;
+  uint32_t ra[16], rb[16];
+  bool released = false;
+  if (half < UNITS) {
+    ptx::tmem_ld16(taddr + half * 32, ra);
+    ptx::tmem_ld16(taddr + half * 32 + 16, rb);
+  }
+#pragma unroll 1
+  for (int u = half; u < UNITS; u += 2) {
+    const int n = n0 + u * 32;
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]), v[16 + i] = __uint_as_float(rb[i]);
+    if (u + 2 < UNITS) {
+      ptx::tmem_ld16(taddr + (u + 2) * 32, ra);
+      ptx::tmem_ld16(taddr + (u + 2) * 32 + 16, rb);
+    } else {
+      release();
+      released = true;
+    }
+    if (n >= p.N) continue;
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+        v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+      }
+    }
+    if constexpr (MODE == EPI_SNAKE) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 ea = __ldg(reinterpret_cast<const float4*>(p.ea + n + i));
+        const float4 ib = __ldg(reinterpret_cast<const float4*>(p.ib + n + i));
+        const float s0 = ActIO<bf16>::fsin(v[i] * ea.x), s1 = ActIO<bf16>::fsin(v[i + 1] * ea.y);
+        const float s2 = ActIO<bf16>::fsin(v[i + 2] * ea.z), s3 = ActIO<bf16>::fsin(v[i + 3] * ea.w);
+        v[i] = fmaf(s0 * s0, ib.x, v[i]), v[i + 1] = fmaf(s1 * s1, ib.y, v[i + 1]);
+        v[i + 2] = fmaf(s2 * s2, ib.z, v[i + 2]), v[i + 3] = fmaf(s3 * s3, ib.w, v[i + 3]);
+      }
+    }
+    if constexpr (MODE == EPI_MASK) {
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+    }
+    if (m < p.M) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 hb = __floats2bfloat162_rn(v[16 * hlf + 2 * i], v[16 * hlf + 2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        stg256(orow + n + 16 * hlf, w);
+      }
+    }
+  }
+  if (!released) release();
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 implementation.
 template <int BN>
 struct TcCfg {
@@ -926,8 +1007,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow; elect.sync picks the issuing lane) ===========
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(Cfg::BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -948,16 +1029,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
-            ptx::umma_bf16(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
-                           (it > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16_elect(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
+                                 (it > 0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) ptx::umma_commit(&empty_bar[stage]);
-          else ptx::umma_commit_mcast(&empty_bar[stage], cmask);
+          if (CL == 1) ptx::umma_commit_elect(&empty_bar[stage]);
+          else ptx::umma_commit_mcast_elect(&empty_bar[stage], cmask);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        ptx::umma_commit(&tfull_bar[acc]);
+        ptx::umma_commit_elect(&tfull_bar[acc]);
       }
-      if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
+      if (prof && lane == 0) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
       // Programmatic dependent launch: the next kernel may be scheduled once every CTA has issued its last MMA, so its launch
       // latency and prologue overlap this kernel's last epilogue instead of its whole run (an early trigger lets the
       // dependent CTAs sit on SMs that this grid's later tiles still need).
@@ -986,6 +1067,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK) {
+          if (p.direct_epi) {
+            epilogue_tile_direct<BN, MODE>(p, taddr, m0, n0, half, lane, [&] {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            });
+            continue;
+          }
+        }
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK || MODE == EPI_RESID) {
           if (p.tma_epi) {
             epilogue_tile_tma<BN, MODE>(p, &tmOut, taddr, stg, m0, n0, half, lane, [&] {
@@ -1135,8 +1226,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane of the leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (warp 1 of the leader CTA, uniform control flow; elect.sync picks the lane) ======
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * Cfg::BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -1157,17 +1248,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
-            ptx::umma_bf16_pair(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
-                                (it > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16_pair_elect(tmem_d, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (it > 0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit_pair(&empty_bar[stage], 3);  // frees the stage in both CTAs
+          ptx::umma_commit_pair_elect(&empty_bar[stage], 3);  // frees the stage in both CTAs
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        ptx::umma_commit_pair(&tfull_bar[acc], 3);  // accumulator ready in both CTAs
+        ptx::umma_commit_pair_elect(&tfull_bar[acc], 3);  // accumulator ready in both CTAs
       }
-      if (prof) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
+      if (prof && lane == 0) p.prof[2] = (unsigned long long)(clock64() - t_start), p.prof[3] = w_full, p.prof[4] = w_tempty, p.prof[8] = (unsigned long long)local;
     }
-    if (lane == 0) ptx::pdl_launch_dependents();  // leader: after its last MMA; follower: nothing left to issue
+    ptx::pdl_launch_dependents();  // leader: after its last MMA; follower: nothing left to issue
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
     const uint32_t stg = ptx::smem_u32(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES) + (warp - 4) * Cfg::EPI_WARP_BYTES;
@@ -1188,6 +1279,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK) {
+          if (p.direct_epi) {
+            epilogue_tile_direct<BN, MODE>(p, taddr, m0, n0, half, lane, [&] {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+              }
+            });
+            continue;
+          }
+        }
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK || MODE == EPI_RESID) {
           if (p.tma_epi) {
             epilogue_tile_tma<BN, MODE>(p, &tmOut, taddr, stg, m0, n0, half, lane, [&] {

@@ -196,6 +196,58 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_ma
                : "memory");
 }
 
+// Warp-uniform forms: EVERY lane of the issuing warp calls these with identical operands and elect.sync picks the one lane
+// that issues.  Keeping the control flow uniform matters: inside an `if (lane == 0)` branch the compiler cannot prove the
+// descriptors warp-uniform and moves each of them into uniform registers with an ELECT / R2UR.BROADCAST / BRA.U.ANY loop -
+// ~20 dependent instructions per MMA, more than the 96-128 cycles the MMA itself takes (measured 170 cycles per MMA).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- CTA-pair (cta_group::2) variants
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> even CTA of the pair
 

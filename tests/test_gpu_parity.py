@@ -216,10 +216,10 @@ def test_utterances_are_independent_given_T(flags, tol):
     assert rel_l2(solo[0], full[1]) <= tol
 
 
-@pytest.mark.parametrize("tma_mask,pair_mode", [(0, 0), (0, 2), (63, 1), (63, 2), (4, 1)])
-def test_kernel_selection_switches_keep_parity(tma_mask, pair_mode):
+@pytest.mark.parametrize("tma_mask,pair_mode,direct_mask", [(0, 0, 0), (0, 2, 0), (63, 1, 0), (63, 2, 0), (4, 1, 0), (4, 1, 25), (0, 2, 25)])
+def test_kernel_selection_switches_keep_parity(tma_mask, pair_mode, direct_mask):
     """cfm_set_option: every GEMM epilogue / CTA-pair selection (TMA-store epilogue per mode incl. the L2 reduce-add residual,
-    1-CTA vs cta_group::2 kernels) stays within the bf16 tolerance of the oracle on the prod estimator."""
+    direct 256-bit-store epilogue, 1-CTA vs cta_group::2 kernels) stays within the bf16 tolerance of the oracle on the prod estimator."""
     ora, m = pair(syn.PROD, "euler", "bf16")
     lengths = [150, 97, 200, 31]
     mu, mask, z, _ = syn.make_inputs(lengths, seed=5)
@@ -228,8 +228,9 @@ def test_kernel_selection_switches_keep_parity(tma_mask, pair_mode):
     m.refresh(torch.device("cuda", torch.cuda.current_device()))
     m.set_option("tma_epi", tma_mask)
     m.set_option("pair_mode", pair_mode)
+    m.set_option("direct_epi", direct_mask)
     out = m.solve(z.cuda(), ts.cuda(), mu.cuda(), mask.cuda())
-    check(out, ref, "bf16", f"prod euler/4 tma_mask={tma_mask} pair_mode={pair_mode}")
+    check(out, ref, "bf16", f"prod euler/4 tma_mask={tma_mask} pair_mode={pair_mode} direct_mask={direct_mask}")
     with pytest.raises(ValueError):
         m.set_option("no_such_switch", 1)
 
