@@ -130,20 +130,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   //   softmax     : wait S_j -> max -> P_j = exp2(...) -> smem P[b] -> O += PV_{j-1} (finished long ago), O *= corr -> arrive P_j
   // so the softmax warps never wait on an MMA issued in the same iteration.
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer (tiles 0 and 1 were requested in the prologue)
+    {  // ---------------- TMA producer, whole warp in uniform control flow (tiles 0 and 1 were requested in the prologue)
       for (int j = 2; j < n_tiles; ++j) {
         const int b = j & 1;
         const uint32_t prev = ((j >> 1) - 1) & 1;  // parity of the previous use of buffer b
         ptx::mbar_wait(bar_s + b, prev);  // S_{j-2} complete: K[b] free
-        ptx::mbar_expect_tx(bar_k + b, Cfg::K_BYTES);
-        ptx::tma_load_2d(smem + Cfg::OFF_K + b * Cfg::K_BYTES, &tm_kv, bar_k + b, inner + head * Cfg::D, row0 + j * Cfg::KT);
+        ptx::mbar_expect_tx_elect(bar_k + b, Cfg::K_BYTES);
+        ptx::tma_load_2d_elect(smem + Cfg::OFF_K + b * Cfg::K_BYTES, &tm_kv, bar_k + b, inner + head * Cfg::D, row0 + j * Cfg::KT);
         ptx::mbar_wait(bar_pv + b, prev);  // PV_{j-2} complete: V[b] free
-        ptx::mbar_expect_tx(bar_v + b, Cfg::V_BYTES);
-        ptx::tma_load_2d(smem + Cfg::OFF_V + b * Cfg::V_BYTES, &tm_kv, bar_v + b, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+        ptx::mbar_expect_tx_elect(bar_v + b, Cfg::V_BYTES);
+        ptx::tma_load_2d_elect(smem + Cfg::OFF_V + b * Cfg::V_BYTES, &tm_kv, bar_v + b, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
+    {  // ---------------- MMA issuer: whole warp in uniform control flow, elect.sync picks the issuing lane (see ptx.cuh)
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64, 0);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 64, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + Cfg::OFF_Q), k_addr = ptx::smem_u32(smem + Cfg::OFF_K);
@@ -156,9 +156,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16(tmem_base + b * 64, ptx::umma_desc_sw128(q_addr + k * 32),
+          ptx::umma_bf16_elect(tmem_base + b * 64, ptx::umma_desc_sw128(q_addr + k * 32),
                          ptx::umma_desc_sw128(k_addr + b * Cfg::K_BYTES + k * 32), idesc_s, k > 0);
-        ptx::umma_commit(bar_s + b);
+        ptx::umma_commit_elect(bar_s + b);
       };
       mbar_wait_prof(bar_q, 0, do_prof, wq);
       issue_s(0);
@@ -171,13 +171,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16(tmem_pv, ptx::umma_desc_sw128(p_addr + b * Cfg::P_BYTES + k * 32),
+          ptx::umma_bf16_elect(tmem_pv, ptx::umma_desc_sw128(p_addr + b * Cfg::P_BYTES + k * 32),
                          ptx::umma_desc_sw128(v_addr + b * Cfg::V_BYTES + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        ptx::umma_commit(bar_pv + b);
+        ptx::umma_commit_elect(bar_pv + b);
         if (j + 2 < n_tiles) issue_s(j + 2);
       }
       ptx::pdl_launch_dependents();  // last MMA issued: the next kernel's launch overlaps this CTA's final softmax pass and epilogue
-      if (do_prof) {
+      if (do_prof && lane == 0) {
         prof[0] = (unsigned long long)(clock64() - t_start), prof[1] = wq, prof[2] = wk, prof[3] = wp, prof[4] = wv;
         prof[5] = (unsigned long long)n_tiles;
       }

@@ -129,7 +129,7 @@ struct cfm_handle {
                                                 // plans of <= 2048 packed rows: -8 % on cfg1, where launch latency dominates; off
                                                 // above: +0.5-2 % on cfg2 / cfg4), 0 off, 1 on (CFM_B200_PDL, cfm_set_option "pdl")
   int pdl_now = 0;                              // resolved per plan
-  int direct_epi = 0;                           // bit m: direct (256-bit store, no smem) epilogue for bf16-output EpiMode m; "direct_epi"
+  int direct_epi = (1 << EPI_STORE) | (1 << EPI_MASK);  // (-0.1 ms on cfg2; SNAKE is slower this way) bit m: direct (256-bit store, no smem) epilogue for bf16-output EpiMode m; "direct_epi"
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option

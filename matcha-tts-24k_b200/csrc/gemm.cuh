@@ -977,8 +977,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   ptx::pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in uniform control flow; elect.sync picks the issuing lane) =========
+    {
       int stage = 0;
       uint32_t phase = 0;
       const bool prof = p.prof != nullptr && blockIdx.x == 0;
@@ -992,19 +992,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const CUtensorMap* tmA = tap.a_src ? &tmA1 : &tmA0;
           for (int kb = 0; kb < kb_per_tap; ++kb) {
             mbar_wait_prof(&empty_bar[stage], phase ^ 1, prof, w_empty);  // every CTA of the cluster released this stage
-            ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            ptx::mbar_expect_tx_elect(&full_bar[stage], Cfg::STAGE_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            ptx::tma_load_2d(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
+            ptx::tma_load_2d_elect(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
             if (CL == 1)
-              ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
+              ptx::tma_load_2d_elect(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
             else
-              ptx::tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * b_rows * 128, &tmW, &full_bar[stage], kb * Cfg::BK,
-                                     tap.w_row + n0 + crank * b_rows, cmask);
+              ptx::tma_load_2d_mcast_elect(sa + Cfg::A_BYTES + crank * b_rows * 128, &tmW, &full_bar[stage], kb * Cfg::BK,
+                                           tap.w_row + n0 + crank * b_rows, cmask);
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
       }
-      if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
+      if (prof && lane == 0) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp in uniform control flow; elect.sync picks the issuing lane) ===========
@@ -1201,8 +1201,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   ptx::pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane per CTA) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp 0 of each CTA, uniform control flow; elect.sync picks the lane) ===========
+    {
       int stage = 0;
       uint32_t phase = 0;
       const bool prof = p.prof != nullptr && blockIdx.x == 0;
@@ -1215,15 +1215,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const CUtensorMap* tmA = tap.a_src ? &tmA1 : &tmA0;
           for (int kb = 0; kb < kb_per_tap; ++kb) {
             mbar_wait_prof(&empty_bar[stage], phase ^ 1, prof, w_empty);
-            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+            if (rank == 0) ptx::mbar_expect_tx_elect(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            ptx::tma_load_2d_pair(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
-            ptx::tma_load_2d_pair(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
+            ptx::tma_load_2d_pair_elect(sa, tmA, &full_bar[stage], tap.a_col + kb * Cfg::BK, m0 + tap.row_shift);
+            ptx::tma_load_2d_pair_elect(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], kb * Cfg::BK, tap.w_row + n0);
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
       }
-      if (prof) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
+      if (prof && lane == 0) p.prof[0] = (unsigned long long)(clock64() - t_start), p.prof[1] = w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp 1 of the leader CTA, uniform control flow; elect.sync picks the lane) ======
