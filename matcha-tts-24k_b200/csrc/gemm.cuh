@@ -707,7 +707,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   constexpr int UNITS = BN / 32;
   constexpr bool F32 = (MODE == EPI_RESID);
   constexpr int UNIT_BYTES = F32 ? 4096 : 2048;
-  constexpr int GROUP = 8192 / UNIT_BYTES;  // units staged per fence / TMA-issue round (per-warp staging = 8 KB)
+  constexpr int GROUP = 4096 / UNIT_BYTES;  // units staged per fence / TMA-issue round (per-warp staging: 4 KB of the 5 KB slot)
   bool valid = true;
   if constexpr (MODE == EPI_MASK) valid = (load_row_info(p, m0 + lane) & ROW_VALID) != 0;
   uint32_t ra[16], rb[16];
@@ -721,13 +721,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   auto flush = [&]() {   // generic-proxy smem writes -> async proxy, then one lane issues the stores of this round
     ptx::fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
-      for (int i = 0; i < staged; ++i) {
-        if constexpr (F32) ptx::tma_reduce_add_2d(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
-        else ptx::tma_store_2d(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
-      }
-      ptx::bulk_commit();
+    for (int i = 0; i < staged; ++i) {  // warp-uniform: the elected lane issues
+      if constexpr (F32) ptx::tma_reduce_add_2d_elect(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
+      else ptx::tma_store_2d_elect(tm_out, stg + i * UNIT_BYTES, first_n + i * 64, m0);
     }
+    ptx::bulk_commit_elect();
     staged = 0;
   };
 #pragma unroll 1
@@ -776,7 +774,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     }
     // ---- stage; before the first write of a round the previous round's stores must have read the staging area
     if (staged == 0) {
-      if (lane == 0) ptx::bulk_wait_read<0>();
+      ptx::bulk_wait_read_elect<0>();
       __syncwarp();
       first_n = n;
     }
@@ -892,7 +890,7 @@ struct TcCfg {
   static constexpr int CTRL_BYTES = 2048;  // mbarriers + TMEM slot (256 B), GroupNorm partial sums [2 sets][8 warps][8 groups][2] + counters
   static constexpr int N_EPI_WARPS = 8;
   static constexpr int EPI_LD = 36;  // padded row (floats): 16-byte aligned rows, conflict-free 128-bit accesses
-  static constexpr int EPI_WARP_BYTES = 8192;  // per-warp staging: 32 x 36 floats (transposing epilogue) or 1024-aligned TMA-store units
+  static constexpr int EPI_WARP_BYTES = 5120;  // per-warp staging: 32 x 36 floats (transposing epilogue) or 1024-aligned TMA-store units
   static constexpr int EPI_BYTES = N_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -1092,7 +1090,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       }
-      if (p.tma_epi && lane == 0) ptx::bulk_wait_all();  // smem staging is read / global writes land before the CTA exits
+      if (p.tma_epi) ptx::bulk_wait_all_elect();  // smem staging is read / global writes land before the CTA exits
       if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
     };
     switch (p.mode) {
@@ -1134,7 +1132,7 @@ struct Tc2Cfg {
   static constexpr int CTRL_BYTES = 2048;
   static constexpr int N_EPI_WARPS = 8;
   static constexpr int EPI_LD = 36;
-  static constexpr int EPI_WARP_BYTES = 8192;
+  static constexpr int EPI_WARP_BYTES = 5120;
   static constexpr int EPI_BYTES = N_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - CTRL_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -1313,7 +1311,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
         }
       }
-      if (p.tma_epi && lane == 0) ptx::bulk_wait_all();
+      if (p.tma_epi) ptx::bulk_wait_all_elect();
       if (prof && lane == 0) p.prof[5] = (unsigned long long)(clock64() - t_start), p.prof[6] = w_tfull;
     };
     switch (p.mode) {
