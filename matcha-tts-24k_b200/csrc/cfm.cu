@@ -130,6 +130,7 @@ struct cfm_handle {
                                                 // above: +0.5-2 % on cfg2 / cfg4), 0 off, 1 on (CFM_B200_PDL, cfm_set_option "pdl")
   int pdl_now = 0;                              // resolved per plan
   int direct_epi = (1 << EPI_STORE) | (1 << EPI_MASK);  // (-0.1 ms on cfg2; SNAKE is slower this way) bit m: direct (256-bit store, no smem) epilogue for bf16-output EpiMode m; "direct_epi"
+  int pair_n256 = 0;                            // also use the pair kernel for short-K GEMMs with 256-column tiles (FF1); "pair_n256"
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
@@ -528,7 +529,7 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     else CKR(make_out_tmap(h, &tmO, p.out_act, false, p.N, p.M, p.ld_act));
   }
   // CTA-pair kernel where it measures faster: long reductions (k=3 convs, FF2); short-K GEMMs are epilogue-bound there.
-  const bool pair_ok = h->pair_mode == 2 || (h->pair_mode == 1 && p.n_taps * p.K >= 1024);
+  const bool pair_ok = h->pair_mode == 2 || (h->pair_mode == 1 && (p.n_taps * p.K >= 1024 || (h->pair_n256 && bn == 256)));
   p.pair = pair_ok && bn >= 128 ? 1 : 0;
   p.cluster = p.pair ? 1 : h->cluster;
   CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, p.pair ? bn / 2 : bn / p.cluster));
@@ -1470,6 +1471,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
   else if (strcmp(key, "graph_after") == 0 && value >= 0) h->graph_after = value;
+  else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "direct_epi") == 0 && value >= 0) h->direct_epi = value;
   else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
