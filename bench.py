@@ -73,7 +73,7 @@ class ClockSampler:
         return len(self.rows)
 
     def summary(self, lo=0, hi=None):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.rows[lo:hi]:
             f = [x.strip() for x in line.split(",")]
@@ -83,12 +83,17 @@ class ClockSampler:
                 sm.append(float(f[0])), mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None, "power_w_max": max(pw) if pw else None}
 
 
 def workload(name: str):
