@@ -99,11 +99,17 @@ int cfm_set_speakers(cfm_handle* h, const float* spks);
  * Results do not depend on the lane count.  Default 1 lane (measured slower on cfg2-4) / 4096 rows (env CFM_B200_LANES, CFM_B200_LANE_MIN_ROWS). */
 int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
 
-/* Kernel-selection switches for A/B measurements (take effect at the next cfm_plan / debug GEMM): "tma_epi" 0/1 (TMA-store
- * GEMM epilogue), "pair_mode" 0/1/2 (CTA-pair GEMM never / where it measures faster / always), "pdl" -1/0/1 (programmatic dependent launch: auto = small plans only / off /
- * on), "cluster" 1/2/4, "small_tiles" M (GEMMs of at most M rows use 64-column tiles; 0 = never), "graph_after" n (a plan's first n decodes use
- * direct launches, its CUDA graph is captured before decode n + 1; 0 = capture inside cfm_plan; default 1).
- * Results stay within the precision mode's tolerance for every setting. */
+/* Kernel-selection switches for A/B measurements (take effect at the next cfm_plan / debug GEMM).  Results stay within the
+ * precision mode's tolerance for every setting (tests/test_gpu_parity.py).
+ *   "tma_epi"     bit m: TMA-store GEMM epilogue for epilogue mode m (1 = all modes; default: the in-place residual add only)
+ *   "direct_epi"  bit m: 256-bit-store epilogue without shared-memory staging for bf16-output mode m (default: STORE, MASK)
+ *   "pair_mode"   0/1/2: CTA-pair (cta_group::2) GEMM never / for long reductions (default) / always
+ *   "pair_n256"   0/1: also run short-K GEMMs with 256-column tiles (FF1) on the pair kernel
+ *   "cluster"     1/2/4: CTAs sharing one weight tile through TMA multicast in the 1-CTA kernel
+ *   "pdl"         -1/0/1: programmatic dependent launch: automatic (plans of <= 2048 packed rows) / off / on
+ *   "small_tiles" M: GEMMs of at most M rows use 64-column tiles (0 = never; default 1024)
+ *   "graph_after" n: a plan's first n decodes use direct launches, its CUDA graph is captured before decode n + 1
+ *                 (0 = capture inside cfm_plan; default 1) */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
 
 /* Same with HOST buffers (pinned or pageable): H2D of mu and z, solve, D2H of out, then synchronises.
