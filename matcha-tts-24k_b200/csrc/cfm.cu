@@ -131,6 +131,10 @@ struct cfm_handle {
   int pdl_now = 0;                              // resolved per plan
   int direct_epi = (1 << EPI_STORE) | (1 << EPI_MASK);  // (-0.1 ms on cfg2; SNAKE is slower this way) bit m: direct (256-bit store, no smem) epilogue for bf16-output EpiMode m; "direct_epi"
   int pair_n256 = 0;                            // also use the pair kernel for short-K GEMMs with 256-column tiles (FF1); "pair_n256"
+  int l2_persist_mb = 32;                       // persisting-L2 carve-out (MB) for the fp32 residual stream ("l2_persist_mb",
+                                                // CFM_B200_L2_PERSIST_MB; cfg2 sustained: 0 -> 30.65, 32 -> 30.03, 48 -> 30.4, 64 -> 31.8, 79 -> 34.4 ms)
+  void* win_ptr = nullptr;
+  size_t win_bytes = 0, win_max = 0;
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
@@ -235,6 +239,7 @@ int ensure_workspace(cfm_handle* h, size_t need) {
 }
 
 void free_plan(cfm_handle* h) {
+  h->win_bytes = 0;  // the L2 access-policy window points into the plan's workspace
   if (!h->plan) return;
   if (h->plan->exec) cudaGraphExecDestroy(h->plan->exec);
   if (h->plan->graph) cudaGraphDestroy(h->plan->graph);
@@ -431,8 +436,17 @@ int launch_ex(cfm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (h->win_bytes > 0) {  // keep the fp32 residual stream of the current resolution resident in the persisting part of L2
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = h->win_ptr;
+    attr[n].val.accessPolicyWindow.num_bytes = h->win_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
   if (cluster > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
     attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
@@ -771,6 +785,10 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
 
 int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void* A, long long lda, int& site,
               const float* tproj, void* copy_dst, long long copy_ld, cudaStream_t s) {
+  if (h->l2_persist_mb > 0) {  // L2 access-policy window = this stage's fp32 residual stream (read / updated 6x per block)
+    h->win_ptr = R.X;
+    h->win_bytes = std::min((size_t)R.M * h->C() * sizeof(float), h->win_max);
+  }
   // the resnet's last GroupNorm-apply also produces LayerNorm1 of the first transformer block when the width allows
   const bool fuse = h->C() % 128 == 0 && h->C() <= 512 && !w.blocks.empty() && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS);
   CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, s, fuse ? &w.blocks[0].ln1 : nullptr));
@@ -1002,6 +1020,22 @@ int build_stages(cfm_handle* h, Plan* pl, const float* t_span, int n_points, int
   return 0;
 }
 
+// Persisting-L2 carve-out for the fp32 residual stream (launch_ex attaches the access-policy window).  The device limit is
+// process-wide state: it is only ever raised here, never lowered below what somebody else configured.
+int apply_l2_persist(cfm_handle* h, int mb) {
+  h->l2_persist_mb = mb, h->win_bytes = 0, h->win_max = 0;
+  if (mb <= 0) return 0;
+  int max_persist = 0, max_win = 0;
+  CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->cfg.device));
+  CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, h->cfg.device));
+  const size_t want = std::min((size_t)mb << 20, (size_t)max_persist);
+  size_t cur = 0;
+  CK(cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize));
+  if (cur < want) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+  h->win_max = std::min(want, (size_t)max_win);
+  return 0;
+}
+
 int capture_graph(cfm_handle* h, Plan* pl) {
   if (h->cfg.flags & CFM_FLAG_NO_GRAPH) return 0;
   const long long saved = h->launch_counter;
@@ -1086,6 +1120,8 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   r = r ? r : attn_tc_set_attr(&h->err);
   if (r) return bail(r);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }
+  if (const char* e = getenv("CFM_B200_L2_PERSIST_MB")) h->l2_persist_mb = std::max(0, atoi(e));
+  if (apply_l2_persist(h, h->l2_persist_mb) != 0) return bail(CFM_ERR_CUDA);
   *out = h;
   return 0;
 }
@@ -1471,6 +1507,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
   else if (strcmp(key, "graph_after") == 0 && value >= 0) h->graph_after = value;
+  else if (strcmp(key, "l2_persist_mb") == 0 && value >= 0) return apply_l2_persist(h, value);
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "direct_epi") == 0 && value >= 0) h->direct_epi = value;
   else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
