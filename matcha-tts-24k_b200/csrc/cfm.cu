@@ -1544,7 +1544,7 @@ int cfm_debug_gemm_profile(cfm_handle* h, const void* a, const void* w, float* d
   p.prof = prof;
   if (mode == 0) p.mode = EPI_STORE, p.out_act = d_bf16, p.ld_act = N;
   else if (mode == 1) p.mode = EPI_STATS, p.fused_stats = 0, p.out_f32 = d_f32, p.ld_f32 = N;
-  else if (mode >= 3) {  // fp32 store + fused GroupNorm statistics on synthetic 942-row utterances; mode - 3 = debug skip bits << 1
+  else if (mode == 3) {  // fp32 store + fused GroupNorm statistics on synthetic 942-row utterances
     static int* info = nullptr;
     static double* stats = nullptr;
     static float* bias = nullptr;
@@ -1560,7 +1560,7 @@ int cfm_debug_gemm_profile(cfm_handle* h, const void* a, const void* w, float* d
       CK(cudaMemset(bias, 0, 4096 * 4));
       info_rows = M;
     }
-    p.mode = EPI_STATS, p.fused_stats = 1 | ((mode - 3) << 1), p.out_f32 = d_f32, p.ld_f32 = N, p.row_info = info, p.stats = stats;
+    p.mode = EPI_STATS, p.fused_stats = 1, p.out_f32 = d_f32, p.ld_f32 = N, p.row_info = info, p.stats = stats;
     p.group_ch = N / 8, p.bias = bias;
   } else p.mode = EPI_RESID, p.resid = d_f32, p.ld_resid = N, p.out_f32 = d_f32, p.ld_f32 = N;
   const int saved = h->cfg.flags;
