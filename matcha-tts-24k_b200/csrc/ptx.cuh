@@ -39,14 +39,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint of try_wait: the waiting thread is parked by the hardware until the phase completes (or this many ns pass)
+// instead of re-polling - a dozen waiting warps per CTA otherwise burn issue slots and power the capped chip does not have.
+constexpr uint32_t kSuspendHintNs = 0x989680;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
