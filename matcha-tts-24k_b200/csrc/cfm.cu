@@ -135,6 +135,7 @@ struct cfm_handle {
                                                 // CFM_B200_L2_PERSIST_MB; cfg2 sustained: 0 -> 30.65, 32 -> 30.03, 48 -> 30.4, 64 -> 31.8, 79 -> 34.4 ms)
   void* win_ptr = nullptr;
   size_t win_bytes = 0, win_max = 0;
+  int snake_warps = 12;                         // epilogue warps of the SnakeBeta (FF1) GEMM: 8 or 12; "snake_warps"
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
@@ -473,6 +474,14 @@ int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, co
   return launch_ex(h, gemm_tc_kernel<BN>, dim3(clusters * CL), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, CL, a0, a1, w, o, p);
 }
 
+// SnakeBeta GEMM (FF1) with 12 epilogue warps: its epilogue (one MUFU sine + 5 FP32 operations per element) is what bounds it.
+int launch_tc_snake12(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+                      const GemmParams& p, cudaStream_t s) {
+  using Cfg = TcCfg<256, 12>;
+  const int tiles = ((p.M + 127) / 128) * ((p.N + 255) / 256);
+  return launch_ex(h, gemm_tc_kernel<256, 12>, dim3(std::min(tiles, h->max_clusters[1])), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 1, a0, a1, w, o, p);
+}
+
 template <int BN>
 int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
                   const GemmParams& p, cudaStream_t s) {
@@ -555,6 +564,8 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
       default: return launch_tc2_bn<256>(h, tmA[0], tmA[1], tmW, tmO, p, s);
     }
   }
+  if (bn == 256 && p.mode == EPI_SNAKE && h->snake_warps == 12 && p.cluster == 1 && !p.tma_epi && !p.direct_epi)
+    return launch_tc_snake12(h, tmA[0], tmA[1], tmW, tmO, p, s);
   switch (bn) {
     case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, tmO, p, s);
     case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, tmO, p, s);
@@ -1113,6 +1124,10 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   r = r ? r : set_tc_attr<160>(h);
   r = r ? r : set_tc_attr<192>(h);
   r = r ? r : set_tc_attr<256>(h);
+  if (!r && cudaFuncSetAttribute(gemm_tc_kernel<256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, 12>::SMEM_BYTES) != cudaSuccess) {
+    h->err = "cudaFuncSetAttribute(gemm_tc_kernel<256, 12>) failed";
+    r = CFM_ERR_CUDA;
+  }
   r = r ? r : set_tc2_attr<128>(h);
   r = r ? r : set_tc2_attr<160>(h);
   r = r ? r : set_tc2_attr<192>(h);
@@ -1507,6 +1522,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;
   else if (strcmp(key, "graph_after") == 0 && value >= 0) h->graph_after = value;
+  else if (strcmp(key, "snake_warps") == 0 && (value == 8 || value == 12)) h->snake_warps = value;
   else if (strcmp(key, "l2_persist_mb") == 0 && value >= 0) return apply_l2_persist(h, value);
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "direct_epi") == 0 && value >= 0) h->direct_epi = value;

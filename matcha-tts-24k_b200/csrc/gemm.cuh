@@ -637,7 +637,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     ptx::tmem_ld16(taddr + half * 32 + 16, r1);
   }
 #pragma unroll 1
-  for (int blk = half; blk < BN / 32; blk += 2) {
+  constexpr int BLK_STEP = N_EPI_WARPS / 4;  // warps per TMEM lane quarter alternate over the 32-column blocks
+  for (int blk = half; blk < BN / 32; blk += BLK_STEP) {
     const int c = blk * 32;
     ptx::tmem_ld_wait();
     const uint32_t srow = stg + lane * EPI_LD * 4;
@@ -648,9 +649,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
       ptx::sts128(srow + 64 + i * 16, __uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]), __uint_as_float(r1[4 * i + 2]),
                   __uint_as_float(r1[4 * i + 3]));
     }
-    if (blk + 2 < BN / 32) {  // prefetch the next block's accumulators while this one goes out to global memory
-      ptx::tmem_ld16(taddr + c + 64, r0);
-      ptx::tmem_ld16(taddr + c + 64 + 16, r1);
+    if (blk + BLK_STEP < BN / 32) {  // prefetch the next block's accumulators while this one goes out to global memory
+      ptx::tmem_ld16(taddr + c + 32 * BLK_STEP, r0);
+      ptx::tmem_ld16(taddr + c + 32 * BLK_STEP + 16, r1);
     }
     __syncwarp();
     if constexpr (WIDE) {
@@ -880,7 +881,7 @@ __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 implementation.
-template <int BN>
+template <int BN, int NEW = 8>  // NEW = epilogue warps (8, or 12 for the SnakeBeta GEMM whose epilogue is the bottleneck)
 struct TcCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -888,7 +889,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_SMEM = 227 * 1024;
   static constexpr int CTRL_BYTES = 2048;  // mbarriers + TMEM slot (256 B), GroupNorm partial sums [2 sets][8 warps][8 groups][2] + counters
-  static constexpr int N_EPI_WARPS = 8;
+  static constexpr int N_EPI_WARPS = NEW;
   static constexpr int EPI_LD = 36;  // padded row (floats): 16-byte aligned rows, conflict-free 128-bit accesses
   static constexpr int EPI_WARP_BYTES = 5120;  // per-warp staging: 32 x 36 floats (transposing epilogue) or 1024-aligned TMA-store units
   static constexpr int EPI_BYTES = N_EPI_WARPS * EPI_WARP_BYTES;
@@ -912,11 +913,11 @@ __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, b
   acc += (unsigned long long)(clock64() - t0);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
+template <int BN, int NEW = 8>
+__global__ void __launch_bounds__(TcCfg<BN, NEW>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, NEW>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1066,7 +1067,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK) {
-          if (p.direct_epi) {
+          if (NEW == 8 && p.direct_epi) {
             epilogue_tile_direct<BN, MODE>(p, taddr, m0, n0, half, lane, [&] {
               ptx::tc_fence_before();
               __syncwarp();
@@ -1076,7 +1077,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK || MODE == EPI_RESID) {
-          if (p.tma_epi) {
+          if (NEW == 8 && p.tma_epi) {
             epilogue_tile_tma<BN, MODE>(p, &tmOut, taddr, stg, m0, n0, half, lane, [&] {
               ptx::tc_fence_before();
               __syncwarp();

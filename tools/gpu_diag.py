@@ -180,6 +180,7 @@ def c_epimodes():
         m.set_option("direct_epi", f[5] if len(f) > 5 else 0)
         m.set_option("pair_n256", f[6] if len(f) > 6 else 0)
         m.set_option("l2_persist_mb", f[7] if len(f) > 7 else 0)
+        m.set_option("snake_warps", f[8] if len(f) > 8 else 12)
         reps = int(os.environ.get("DIAG_REPS", "5"))
         warm_s = float(os.environ.get("DIAG_WARM_S", "0"))  # > 0: sustained measurement (the decode is power-capped after ~1 s)
         import time as _t
@@ -196,7 +197,7 @@ def c_epimodes():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"[epimodes tma_mask={tma} pair_mode={pair} pdl={f[2] if len(f) > 2 else 0} small_tiles={f[3] if len(f) > 3 else 1024} cluster={f[4] if len(f) > 4 else 1} direct_epi={f[5] if len(f) > 5 else 0} pair_n256={f[6] if len(f) > 6 else 0} l2_persist_mb={f[7] if len(f) > 7 else 0}] {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s "
+        print(f"[epimodes tma_mask={tma} pair_mode={pair} pdl={f[2] if len(f) > 2 else 0} small_tiles={f[3] if len(f) > 3 else 1024} cluster={f[4] if len(f) > 4 else 1} direct_epi={f[5] if len(f) > 5 else 0} pair_n256={f[6] if len(f) > 6 else 0} l2_persist_mb={f[7] if len(f) > 7 else 0} snake_warps={f[8] if len(f) > 8 else 12}] {ms:.2f} ms/solve {P.synthetic.algorithmic_flops(lengths, 384, 10)/ms/1e9:.1f} TFLOP/s "
               f"finite={bool(torch.isfinite(out).all())}", flush=True)
 
 
