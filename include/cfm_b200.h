@@ -110,6 +110,7 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *   "small_tiles" M: GEMMs of at most M rows use 64-column tiles (0 = never; default 1024)
  *   "l2_persist_mb" MB: persisting-L2 carve-out whose access-policy window follows the fp32 residual stream of the stage being
  *                 computed (default 32; 0 = off).  Raises the process-wide cudaLimitPersistingL2CacheSize if it is lower.
+ *   "snake_warps" 8/12: epilogue warps of the SnakeBeta (FF1) GEMM (default 12)
  *   "graph_after" n: a plan's first n decodes use direct launches, its CUDA graph is captured before decode n + 1
  *                 (0 = capture inside cfm_plan; default 1) */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
