@@ -37,7 +37,7 @@ def load_golden(name):
     return case
 
 
-GOLDEN_CASES = ["tiny_euler", "tiny_midpoint", "tiny_rk4_padded", "prod_euler", "default_euler"]
+GOLDEN_CASES = ["tiny_euler", "tiny_midpoint", "tiny_rk4_padded", "tiny_heun3", "prod_euler", "default_euler"]
 
 
 def cfm_params(solver="euler"):

@@ -70,6 +70,10 @@ def _install_third_party_shims():
             elif method == "midpoint":
                 half_dt = 0.5 * dt
                 dy = dt * func(t0 + half_dt, y + f0 * half_dt)
+            elif method == "heun3":  # torchdiffeq fixed_grid.Heun3: tableau c = (0, 1/3, 2/3), b = (1/4, 0, 3/4)
+                k2 = func(t0 + dt / 3, y + dt * f0 / 3)
+                k3 = func(t0 + dt * 2 / 3, y + dt * k2 * 2 / 3)
+                dy = dt * (f0 + 3 * k3) * 0.25
             elif method == "rk4":
                 k2 = func(t0 + dt / 3, y + dt * f0 / 3)
                 k3 = func(t0 + dt * 2 / 3, y + dt * (k2 - f0 / 3))
@@ -109,6 +113,8 @@ CASES = {
                            num_heads=2), [21, 38], 38, "midpoint", 2),
     "tiny_rk4_padded": (dict(channels=(64, 64), dropout=0.05, attention_head_dim=32, n_blocks=2, num_mid_blocks=1,
                              num_heads=2), [9, 14], 20, "rk4", 1),
+    "tiny_heun3": (dict(channels=(64, 64), dropout=0.05, attention_head_dim=32, n_blocks=1, num_mid_blocks=1,
+                        num_heads=2), [19, 26], 26, "heun3", 2),
     "prod_euler": (dict(channels=(384, 384), dropout=0.05, attention_head_dim=64, n_blocks=2, num_mid_blocks=2,
                         num_heads=6), [30, 21], 30, "euler", 2),
     "default_euler": (dict(channels=(320, 320), dropout=0.05, attention_head_dim=64, n_blocks=2, num_mid_blocks=2,
@@ -124,7 +130,10 @@ def main():
 
     import matcha_tts_24k_b200.synthetic as syn
 
+    only = set(sys.argv[1:])
     for name, (dec, lengths, T, solver, n_steps) in CASES.items():
+        if only and name not in only:
+            continue
         cfm_params = types.SimpleNamespace(solver=solver, sigma_min=1e-4, use_mu_prior=True)
         ref = RefCFM(in_channels=200, out_channel=100, cfm_params=cfm_params, decoder_params=dec).eval()
         syn.fill_named_seed(ref.estimator, seed=1234)
