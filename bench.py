@@ -124,27 +124,130 @@ def cpu_oracle_throughput(lengths, n_timed: int, threads: int):
     return sum(lengths) / statistics.median(times), statistics.median(times)
 
 
+def workload_config(desc, args, T):
+    """`config` of the JSON line: names the workload only, identical for both arms."""
+    return {"workload": desc, "estimator": "prod C=384 H=6 d=64 n_blocks=2 mid=2 (37.03 M params, random init + N(0,0.1) 1-D)",
+            "ode": f"{args.solver} x{args.ode_steps}", "spks": args.spks, "t_pad": T,
+            "l2": "activations of one decode exceed the 126 MB L2 (cfg2 workspace 667 MiB): no flush between steps"}
+
+
 def run_reference(args, rank):
+    """Reference arm: the reference's own CPU implementation of the path = the oracle restatement (the
+    reference is not importable here), all host threads, one STEP = one full decode of a bounded SAMPLE of the workload
+    (2 utterances); exactly --warmup untimed and --steps timed steps."""
     if rank != 0:
         return
+    import matcha_tts_24k_b200 as P
+    from oracle import cfm_oracle as O
     threads = len(os.sched_getaffinity(0))
     lengths, desc = workload(args.workload)
+    T = 2 * ((max(lengths) + 1) // 2)
     sample = lengths[:2] if len(lengths) > 2 else lengths  # bounded sample of the same workload
     torch.set_num_threads(threads)
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_throughput(sample, 1, threads)
-    fps, sec = cpu_oracle_throughput(sample, max(1, min(args.steps, 3)), threads)
+    cp = types.SimpleNamespace(solver=args.solver, sigma_min=1e-4, use_mu_prior=True)
+    ora = O.CFM(200 + args.spks, 100, cp, P.synthetic.PROD).eval()
+    mu, mask, z, _ = P.synthetic.make_inputs(sample, seed=1, T=T if args.workload != "cfg3" else None)
+    ts = torch.linspace(0, 1, args.ode_steps + 1)
+    spks = torch.randn(len(sample), args.spks, generator=torch.Generator().manual_seed(3)) if args.spks else None
+    step = (lambda: ora.solve(z, ts, mu, mask, spks)) if args.spks else (lambda: ora.solve(z, ts, mu, mask))
+    for _ in range(args.warmup):
+        step()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    fps = sum(sample) / sec
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "estimator": "prod C=384 H=6 d=64", "ode": "euler x10",
-                       "note": "reference CPU path = oracle restatement of the reference PyTorch CFM; the reference itself is "
-                               "not importable here (torchdiffeq/diffusers absent) and hard-codes CUDA"},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(desc, args, T),
+            "note": "reference CPU path = oracle restatement of the reference PyTorch CFM (the reference itself is not importable "
+                    "here: torchdiffeq / diffusers absent, and it hard-codes CUDA); value = frames of the sample / mean step time",
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{len(sample)} utterance(s) of {desc}, full 10-step decode, median of {max(1, min(args.steps, 3))}"},
+                             "sample": f"each step = full {args.ode_steps}-step {args.solver} decode of {len(sample)} utterance(s) "
+                                       f"({sum(sample)} frames) of {desc}; {args.steps} timed steps, mean"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "rtf": sec / (sum(sample) * FRAME_SECONDS)}
     print(json.dumps(line), flush=True)
+
+
+def gpu_pytorch_baseline(dev, names=("cfg2", "cfg1"), n_timed=5, with_compile=True):
+    """The baseline SURVEY.md section 2a names: the reference's PyTorch path (oracle restatement) on the SAME B200 - eager fp32,
+    eager under torch.autocast(bf16), and with the estimator wrapped in torch.compile(dynamic=True) as reference server.py:47
+    does.  Full 10-step Euler decode, CUDA-event timed; runs after (never inside) the repo arm's timed regions."""
+    import matcha_tts_24k_b200 as P
+    from oracle import cfm_oracle as O
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    ora = O.CFM(200, 100, cp, P.synthetic.PROD).eval().to(dev)
+    out = {}
+
+    def time_it(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    for name in names:
+        lengths, desc = workload(name)
+        mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device=dev)
+        ts = torch.linspace(0, 1, N_STEPS_ODE + 1, device=dev)
+        rec = {"workload": desc, "frames": sum(lengths)}
+        try:
+            ms = time_it(lambda: ora.solve(z, ts, mu, mask), n_timed)
+            rec["eager_fp32"] = {"ms_per_decode": ms, "value": sum(lengths) / ms * 1e3, "unit": UNIT}
+
+            def amp():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return ora.solve(z, ts, mu, mask)
+            ms = time_it(amp, n_timed)
+            rec["eager_autocast_bf16"] = {"ms_per_decode": ms, "value": sum(lengths) / ms * 1e3, "unit": UNIT}
+        except Exception as e:  # noqa: BLE001 - a baseline must never take the bench down
+            rec["error"] = f"{type(e).__name__}: {e}"[:300]
+        out[name] = rec
+    if with_compile:
+        try:
+            t0 = time.perf_counter()
+            eager = ora.estimator
+            ora.estimator = torch.compile(eager, dynamic=True)  # reference server.py:47
+            for name in names:
+                lengths, _ = workload(name)
+                mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device=dev)
+                ts = torch.linspace(0, 1, N_STEPS_ODE + 1, device=dev)
+
+                def amp_c():
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return ora.solve(z, ts, mu, mask)
+                ms = time_it(amp_c, n_timed)
+                out[name]["compile_autocast_bf16"] = {"ms_per_decode": ms, "value": sum(lengths) / ms * 1e3, "unit": UNIT}
+            out["compile_s"] = round(time.perf_counter() - t0, 1)
+            ora.estimator = eager
+        except Exception as e:  # noqa: BLE001
+            out["compile_error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
+def kernel_table(rows, peak_tflops):
+    """Aggregates cfm_debug_timeline rows by launch class: in-situ time, share of the step, achieved TFLOP/s."""
+    agg = {}
+    for tag, M, N, K, flops, us in rows:
+        a = agg.setdefault(tag, {"launches": 0, "us": 0.0, "flops": 0.0})
+        a["launches"] += 1
+        a["us"] += us
+        a["flops"] += flops
+    total = sum(a["us"] for a in agg.values()) or 1.0
+    table = []
+    for tag, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        tf = a["flops"] / (a["us"] * 1e-6) / 1e12 if a["us"] > 0 else 0.0
+        table.append({"kernel": tag, "launches": a["launches"], "ms": a["us"] / 1e3, "share": a["us"] / total,
+                      "tflops": tf, "frac": tf / peak_tflops})
+    return table, total / 1e3
 
 
 def main():
@@ -157,6 +260,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-on-the-same-GPU baseline leg")
+    ap.add_argument("--no-compile-baseline", action="store_true", help="skip the torch.compile part of that leg")
     ap.add_argument("--ode-steps", type=int, default=N_STEPS_ODE, help="Euler steps per decode (BASELINE config 5 sweeps 2/4/10/32)")
     ap.add_argument("--solver", default="euler", choices=["euler", "midpoint", "heun3", "rk4"],
                     help="fixed-grid solver (the reference ships midpoint with 4 steps: matcha/inference.py:39-40)")
@@ -225,7 +330,9 @@ def main():
         return float(t[0]), float(t[1]), out
 
     dev_step = lambda: model.solve(z, ts, mu, mask, lengths=lengths, spks=spks)
-    host_step = (lambda: model.solve_host(z_h, ts, mu_h, lengths, device=dev)) if not args.spks else dev_step
+    out_pinned = torch.empty_like(mu_h).pin_memory()  # the caller's result buffer (pinned: asynchronous device-to-host copy)
+    spks_h = spks.cpu() if spks is not None else None
+    host_step = lambda: model.solve_host(z_h, ts, mu_h, lengths, device=dev, spks=spks_h, out=out_pinned)
     # The sampler (an nvidia-smi child) starts BEFORE the warm-up so that its start-up never lands in the timed region;
     # only the samples taken between the two marks are reported.
     with ClockSampler(local_rank) as clk:
@@ -248,6 +355,37 @@ def main():
         raise SystemExit("bench.py: non-finite decode output")
 
     info = model.plan_info()
+    # ---- the call the reference's callers make: CFM.forward(mu, mask, n) with device tensors (mask -> lengths on the host, seed-42
+    # noise, cached time grid): matcha/inference.py:169.  Also for cfg1 (B = 1, the server's request shape) incl. never-seen lengths.
+    fwd = {}
+    if not args.spks and args.solver == "euler":
+        for _ in range(2):
+            model(mu, mask, args.ode_steps)
+        ms_f, _, _ = timed(lambda: model(mu, mask, args.ode_steps), max(3, args.steps // 2))
+        fwd[args.workload] = {"ms_per_call": ms_f / max(3, args.steps // 2), "api": "CFM.forward(mu, mask, n_timesteps), device tensors"}
+        if world == 1:
+            mu1, mask1, _, _ = P.synthetic.make_inputs([150], seed=2, device=dev)
+            for _ in range(3):
+                model(mu1, mask1, N_STEPS_ODE)
+            ms1, _, _ = timed(lambda: model(mu1, mask1, N_STEPS_ODE), 20)
+            news = []
+            for L in (131, 163, 197, 211, 89, 240):  # first request of a length: plan (tables + workspace) + direct-launch decode
+                mu_n, mask_n, _, _ = P.synthetic.make_inputs([L], seed=3, device=dev)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                model(mu_n, mask_n, N_STEPS_ODE)
+                torch.cuda.synchronize(dev)
+                news.append((time.perf_counter() - t0) * 1e3)
+            fwd["cfg1"] = {"ms_per_call": ms1 / 20, "ms_first_call_new_length": statistics.median(news),
+                           "api": "CFM.forward, B=1 L=150, 10 Euler steps (graph replay) / six never-seen lengths (wall clock, median)"}
+            model.solve(z, ts, mu, mask, lengths=lengths, spks=spks)  # make the benchmark plan current again
+    # ---- in-situ per-kernel times of one direct-launch decode (cfm_debug_timeline), for roofline.kernel
+    ktable, k_total_ms = [], None
+    try:
+        rows = model.timeline(z, ts, mu, lengths) if not args.spks else []
+        ktable, k_total_ms = kernel_table(rows, peaks()["tflops_sustained"])
+    except Exception as e:  # noqa: BLE001
+        ktable = [{"error": f"{type(e).__name__}: {e}"[:200]}]
     ms_step = ms_total / args.steps
     value = job_frames / (ms_step * 1e-3)
     e2e_ms = wall_ms_e2e / args.steps
@@ -265,24 +403,36 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": desc, "estimator": "prod C=384 H=6 d=64 n_blocks=2 mid=2 (37.03 M params, random init + N(0,0.1) 1-D)",
-                   "ode": f"{args.solver} x{args.ode_steps}, one CUDA graph", "spks": args.spks, "batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "t_pad": T,
-                   "rows_full": info["rows_full"], "l2": f"workspace {info['workspace_bytes'] / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
-                   "parallelism": "utterance-sharded replicas, no collective" if world > 1 else "single GPU"},
+        "config": workload_config(desc, args, T),
+        "run": {"batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "rows_full": info["rows_full"],
+                "workspace_mib": round(info["workspace_bytes"] / 2**20), "schedule": "whole ODE loop = one CUDA graph",
+                "parallelism": "utterance-sharded replicas, no collective" if world > 1 else "single GPU"},
         "rtf": (ms_step * 1e-3) / (job_frames * FRAME_SECONDS),
         "e2e": {"value": job_frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * n_bytes, "d2h_bytes_per_step": n_bytes, "api": "cfm_solve_host (C ABI, pinned host buffers)" if not args.spks else "device-resident (no host-buffer entry with spks)"},
+                "h2d_bytes_per_step": 2 * n_bytes, "d2h_bytes_per_step": n_bytes, "api": "cfm_solve_host (C ABI, pinned host buffers)" if not args.spks else "cfm_solve_host_spks (C ABI, pinned host buffers)"},
         "gpu_launches": int(info["kernels_per_solve"]) * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + ", sustained bf16",
-                     "kernel": "whole decode = one graph launch (gemm_tc_kernel + attn_tc_kernel carry >97% of the FLOPs)",
+                     "scope": "whole decode = one graph launch (the tensor-core GEMM and attention kernels carry > 97 % of the FLOPs)",
                      "algorithmic_flops_per_launch": flops},
         "clocks": clocks,
     }
+    dom = next((k for k in ktable if k.get("tflops", 0) > 0), None)
+    if dom:  # the launch class with the largest share of the step, timed in situ (direct launches, one event per launch)
+        line["roofline"].update({"kernel": dom["kernel"], "kernel_achieved": dom["tflops"], "kernel_frac": dom["frac"],
+                                 "kernel_share_of_step": dom["share"], "kernel_launches_per_step": dom["launches"],
+                                 "kernel_timing": "CUDA events around every launch of one direct-launch decode (cfm_debug_timeline)"})
+    line["kernels"] = {"timeline_ms": k_total_ms, "by_launch_class": ktable}
+    if fwd:
+        line["forward_api"] = fwd
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and args.workload == "cfg2" and not args.spks:
+        model.close()  # release the workspace before PyTorch allocates its own activations
+        line["gpu_pytorch_baseline"] = gpu_pytorch_baseline(dev, with_compile=not args.no_compile_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
         sample = lengths[:2]
         fps, sec = cpu_oracle_throughput(sample, 2, threads)
+        torch.set_num_threads(threads)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{len(sample)} utterances of {desc}, full 10-step Euler decode, median of 2 (~{2 * sec:.0f} s)"}
     if rank == 0:

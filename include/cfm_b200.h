@@ -76,14 +76,18 @@ int cfm_load_weights(cfm_handle* h, const cfm_weight_desc* descs, int32_t n);
  * matcha/utils/model.py:15-21) with valid lengths `lengths[b]` (prefix masks, reference
  * matcha/utils/model.py:7-9) over the time grid `t_span[0..n_points)` with a torchdiffeq fixed-grid solver
  * (call site flow_matching.py:60-63).  Builds the packed row tables and the workspace; the CUDA graph of the
- * whole ODE loop is captured when the plan is reused (option "graph_after").  Replaces the per-call setup of BASECFM.solve + OdeSolverWrapper. */
+ * whole ODE loop is captured when the plan is reused (option "graph_after").  Plans are cached per handle by
+ * (lengths, t_pad, t_span, solver): planning a shape seen before only makes that plan current.  No device synchronisation:
+ * set-up work runs on the handle's own stream and later calls are ordered behind it.  Replaces the per-call setup of
+ * BASECFM.solve + OdeSolverWrapper. */
 int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad, const float* t_span, int32_t n_points,
              int32_t solver);
 
 /* Replaces: BASECFM.solve(x, t_span, mu, mask) (flow_matching.py:60-63) for the planned shapes.
  * mu, z, out: device fp32, contiguous (batch, out_channels, t_pad).  `z` is the initial state (the injected
  * noise); padded frames of `out` equal `z` there, exactly as in the reference where the masked velocity never
- * moves them.  Asynchronous on `stream`. */
+ * moves them.  Asynchronous on `stream`.  A handle owns one workspace per plan: calls issued on different streams are
+ * ordered one after the other by the library (an event recorded after each enqueue), never run concurrently. */
 int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* stream);
 
 /* Upstream Matcha-TTS speaker conditioning (the fork removed it: documentation/PROBLEMS.md:41-46; BASELINE config 5 names
@@ -112,16 +116,25 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *                 computed (default 32; 0 = off).  Raises the process-wide cudaLimitPersistingL2CacheSize if it is lower.
  *   "snake_warps" 8/12: epilogue warps of the SnakeBeta (FF1) GEMM (default 12)
  *   "graph_after" n: a plan's first n decodes use direct launches, its CUDA graph is captured before decode n + 1
- *                 (0 = capture inside cfm_plan; default 1) */
+ *                 (0 = capture inside cfm_plan; default 1)
+ *   "plan_cache"  n: plans (row tables + workspace + CUDA graph) kept per handle, least recently used evicted (default 8);
+ *                 the only option that does not drop the cached plans */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
 
 /* Same with HOST buffers (pinned or pageable): H2D of mu and z, solve, D2H of out, then synchronises.
- * This is the call a non-PyTorch host (cgo / JNI / N-API) binds. */
+ * This is the call a non-PyTorch host (cgo / JNI / N-API) binds.  Fails with CFM_ERR_INVALID for an estimator with speaker
+ * channels (use cfm_solve_host_spks); never reuses a pointer left by cfm_set_speakers. */
 int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out);
+/* cfm_solve_host for an estimator with S = in_channels - 2 * out_channels > 0 speaker channels: spks = host fp32 (batch, S). */
+int cfm_solve_host_spks(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out);
 
 /* Replaces: one call of Decoder.forward(x, mask, mu, t) (decoder.py:359-426) for the planned shapes:
  * v = estimator(x, mask, mu, t); padded frames of v are zero.  Asynchronous on `stream`. */
 int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream);
+/* Same with the time given as a HOST array of n_t values: n_t = 1 (one t for the batch, as the ODE solver passes it) or
+ * n_t = batch (one t per utterance: the estimator call of the training forward, BASECFM.compute_loss,
+ * flow_matching.py:84-97, where t has shape (B,)).  The array is consumed before the call returns. */
+int cfm_estimator_t(cfm_handle* h, const float* x, const float* mu, const float* t_host, int32_t n_t, float* v, void* stream);
 
 /* Introspection for tests and the benchmark. */
 int cfm_plan_info(const cfm_handle* h, int64_t* rows_full, int64_t* rows_half, int64_t* n_nfe, int64_t* kernels_per_solve,
@@ -135,6 +148,10 @@ int cfm_debug_stop_after(cfm_handle* h, int64_t n_launches);
  * D[m,n] = sum_t sum_k A[m + shift[t], k] * W[t*N + n, k]; A (M x K), W (n_taps*N x K) bf16 device, D fp32. */
 int cfm_debug_gemm(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, int32_t M, int32_t N, int32_t K,
                    int32_t n_taps, const int32_t* shifts, int32_t use_tc, void* stream);
+/* Measurement: one decode of the current plan with direct launches and a CUDA event before every launch.  buf receives one
+ * text line per launch, in order: "tag,M,N,K,flops,us" (us = time to the next mark).  In-situ per-kernel times for bench.py's
+ * roofline.kernel (the ncu launch lists are cold-cache and serialised).  Synchronises `stream`. */
+int cfm_debug_timeline(cfm_handle* h, const float* mu, const float* z, float* out, char* buf, int64_t cap, void* stream);
 /* Debug: every later attn_tc_kernel launch (direct launches only) writes CTA 0's cycle counters to prof_dev[0..16). */
 int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev);
 /* Debug: tensor-core GEMM in one epilogue mode (0 bf16 store, 1 fp32 store, 2 fp32 in-place residual add) with per-role

@@ -11,7 +11,8 @@ PREC = {"bf16": 0, "fp32": 1}
 SOLVERS = {"euler": 0, "midpoint": 1, "heun3": 2, "rk4": 3}
 FLAG_NO_GRAPH, FLAG_SIMT_GEMM, FLAG_UNFUSED_STATS, FLAG_SIMT_ATTN = 1, 2, 4, 8
 EXPORTS = ["cfm_create", "cfm_destroy", "cfm_last_error", "cfm_load_weights", "cfm_plan", "cfm_solve", "cfm_solve_host",
-           "cfm_estimator", "cfm_plan_info", "cfm_debug_read", "cfm_debug_gemm", "cfm_debug_stop_after", "cfm_debug_gemm_profile", "cfm_debug_attn_profile", "cfm_set_speakers", "cfm_set_lanes", "cfm_set_option"]
+           "cfm_estimator", "cfm_plan_info", "cfm_debug_read", "cfm_debug_gemm", "cfm_debug_stop_after", "cfm_debug_gemm_profile", "cfm_debug_attn_profile", "cfm_set_speakers", "cfm_set_lanes", "cfm_set_option",
+           "cfm_solve_host_spks", "cfm_estimator_t", "cfm_debug_timeline"]
 
 
 class Config(C.Structure):
@@ -49,6 +50,9 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.cfm_solve.argtypes = [vp, vp, vp, vp, vp]
     lib.cfm_solve_host.argtypes = [vp, vp, vp, vp]
     lib.cfm_estimator.argtypes = [vp, vp, vp, C.c_float, vp, vp]
+    lib.cfm_estimator_t.argtypes = [vp, vp, vp, C.POINTER(C.c_float), i32, vp, vp]
+    lib.cfm_solve_host_spks.argtypes = [vp, vp, vp, vp, vp]
+    lib.cfm_debug_timeline.argtypes = [vp, vp, vp, vp, C.c_char_p, C.c_int64, vp]
     lib.cfm_plan_info.argtypes = [vp, i64p, i64p, i64p, i64p, i64p]
     lib.cfm_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_int64, i64p, i64p]
     lib.cfm_debug_gemm_profile.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), i32, vp, vp]

@@ -25,13 +25,14 @@ def lengths_from_mask(mask: torch.Tensor):
                          "the float (additive) mask every reference caller passes")
     m = mask[:, 0, :] if mask.ndim == 3 else mask
     T = m.shape[-1]
-    lengths = m.sum(-1).round().to(torch.int64)
-    expect = (torch.arange(T, device=m.device).unsqueeze(0) < lengths.unsqueeze(1)).to(m.dtype)
-    ok = bool(torch.equal(m, expect))
-    lengths = lengths.tolist()
-    if not ok:
+    nz = m != 0  # counted as integers: a bf16 / fp16 mask would round its own sum above 256 / 2048 frames
+    lengths = nz.sum(-1, dtype=torch.int64)
+    is_prefix = (nz == (torch.arange(T, device=m.device).unsqueeze(0) < lengths.unsqueeze(1))).all()
+    is_01 = ((m == 0) | (m == 1)).all()
+    packed = torch.cat([lengths, (is_prefix & is_01).to(torch.int64).reshape(1)]).tolist()  # one device-to-host copy
+    if not packed[-1]:
         raise ValueError("mask is not a 0/1 prefix (sequence) mask")
-    return lengths
+    return packed[:-1]
 
 
 class CFM(torch.nn.Module):
@@ -187,60 +188,130 @@ class CFM(torch.nn.Module):
         """reference flow_matching.py:60-63; ``x`` is the injected initial state z.  ``spks`` (B, S): upstream-style
         speaker conditioning, only for an estimator built with in_channels = 2*n_feats + S."""
         mu_, x_ = self._prep(mu), self._prep(x)
-        B, F, T = mu_.shape
-        spk_dim = self._weights.cfg.in_channels - 2 * self._weights.cfg.out_channels
-        if (spks is None) != (spk_dim == 0):
-            raise ValueError(f"estimator has {spk_dim} speaker channels but spks is {'missing' if spks is None else 'given'}")
-        spks_ = None
-        if spks is not None:
-            spks_ = self._prep(spks)
-            if tuple(spks_.shape) != (B, spk_dim):
-                raise ValueError(f"spks must have shape ({B}, {spk_dim})")
-        if x_.shape != mu_.shape or mask.shape[0] != B or mask.shape[-1] != T:
+        B, F, T = self._check_shapes(mu_, x_)
+        spks_ = self._check_spks(spks, B, prep=True)
+        if mask is not None and (mask.shape[0] != B or mask.shape[-1] != T):
             raise ValueError("x, mu and mask disagree on (B, F, T)")
-        if lengths is None:
-            lengths = lengths_from_mask(mask)
+        lengths = self._check_lengths(lengths if lengths is not None else lengths_from_mask(mask), B, T)
         ts = self._t_list(t_span)
-        lib, handle = self._ensure(mu_.device, [int(v) for v in lengths], T, ts, self.solver)
+        lib, handle = self._ensure(mu_.device, lengths, T, ts, self.solver)
         out = torch.empty_like(mu_)
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
         N.check(lib, handle, lib.cfm_set_speakers(handle, spks_.data_ptr() if spks_ is not None else None))
         N.check(lib, handle, lib.cfm_solve(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr(), stream))
         return out
 
-    @torch.inference_mode()
-    def solve_host(self, x, t_span, mu, lengths, device=None):
-        """Host-buffer entry (cfm_solve_host): CPU tensors in, CPU tensor out, copies inside the library call."""
-        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        mu_, x_ = mu.detach().float().contiguous(), x.detach().float().contiguous()
+    # ------------------------------------------------------------------ argument checks (the library trusts its pointers)
+    def _check_shapes(self, mu_, x_):
+        """The library packs with its own F / B / T: a tensor of another shape would be read out of bounds, where the
+        reference raises a conv shape error."""
+        if mu_.ndim != 3:
+            raise ValueError(f"mu must have shape (B, n_feats, T), got {tuple(mu_.shape)}")
         B, F, T = mu_.shape
+        if F != self._weights.cfg.out_channels:
+            raise ValueError(f"mu has {F} mel channels, this estimator was built for {self._weights.cfg.out_channels}")
+        if tuple(x_.shape) != tuple(mu_.shape):
+            raise ValueError(f"x {tuple(x_.shape)} and mu {tuple(mu_.shape)} disagree on (B, F, T)")
+        return B, F, T
+
+    def _check_spks(self, spks, B, prep):
+        spk_dim = self._weights.cfg.in_channels - 2 * self._weights.cfg.out_channels
+        if (spks is None) != (spk_dim == 0):
+            raise ValueError(f"estimator has {spk_dim} speaker channels but spks is {'missing' if spks is None else 'given'}")
+        if spks is None:
+            return None
+        spks_ = self._prep(spks) if prep else spks.detach().float().contiguous()
+        if tuple(spks_.shape) != (B, spk_dim):
+            raise ValueError(f"spks must have shape ({B}, {spk_dim}), got {tuple(spks_.shape)}")
+        return spks_
+
+    @staticmethod
+    def _check_lengths(lengths, B, T):
+        lengths = [int(v) for v in lengths]
+        if len(lengths) != B:
+            raise ValueError(f"lengths has {len(lengths)} entries for a batch of {B}")
+        if any(v < 1 or v > T for v in lengths):
+            raise ValueError(f"lengths must lie in [1, T={T}]")
+        return lengths
+
+    @torch.inference_mode()
+    def solve_host(self, x, t_span, mu, lengths, device=None, spks=None, out=None):
+        """Host-buffer entry (cfm_solve_host): CPU tensors in, CPU tensor out, copies inside the library call.  Returns a new
+        tensor unless ``out=`` (same shape, fp32, contiguous; pinned memory makes the device-to-host copy asynchronous) is given."""
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if x.is_cuda or mu.is_cuda:
+            raise ValueError("solve_host takes host tensors; use solve() for device tensors")
+        mu_, x_ = mu.detach().float().contiguous(), x.detach().float().contiguous()
+        B, F, T = self._check_shapes(mu_, x_)
+        spks_ = self._check_spks(spks, B, prep=False)
+        lengths = self._check_lengths(lengths, B, T)
         ts = [float(v) for v in torch.as_tensor(t_span, dtype=torch.float32).tolist()]
-        lib, handle = self._ensure(device, [int(v) for v in lengths], T, ts, self.solver)
-        out = getattr(self, "_host_out", None)
-        if out is None or out.shape != mu_.shape or out.is_pinned() != mu_.is_pinned():
-            out = torch.empty_like(mu_, pin_memory=mu_.is_pinned())  # reused across calls: pinning is the slow part
-            object.__setattr__(self, "_host_out", out)
-        N.check(lib, handle, lib.cfm_solve_host(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr()))
+        lib, handle = self._ensure(device, lengths, T, ts, self.solver)
+        if out is None:
+            out = torch.empty_like(mu_)
+        elif out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != tuple(mu_.shape) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous fp32 host tensor of mu's shape")
+        if spks_ is None:
+            N.check(lib, handle, lib.cfm_solve_host(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr()))
+        else:
+            N.check(lib, handle, lib.cfm_solve_host_spks(handle, mu_.data_ptr(), x_.data_ptr(), spks_.data_ptr(), out.data_ptr()))
         return out
 
-    def _estimator_call(self, x, mask, mu, t, spks=None):
+    def _estimator_call(self, x, mask, mu, t, spks=None, lengths=None):
+        """One call of Decoder.forward(x, mask, mu, t) (reference decoder.py:359-426).  ``t``: 0-dim (the ODE solver's call,
+        ode_solver_wrapper.py:11-16) or shape (B,) (the training forward, flow_matching.py:84-97)."""
         mu_, x_ = self._prep(mu), self._prep(x)
-        B, F, T = mu_.shape
-        spks_ = self._prep(spks) if spks is not None else None
-        tt = torch.as_tensor(t)
-        if tt.numel() != 1:
-            raise NotImplementedError("per-sample t (training, reference flow_matching.py:84-97) is not on this path")
-        lengths = lengths_from_mask(mask)
+        B, F, T = self._check_shapes(mu_, x_)
+        spks_ = self._check_spks(spks, B, prep=True)
+        tt = torch.as_tensor(t).detach().to(torch.float32).reshape(-1).cpu()
+        if tt.numel() not in (1, B):
+            raise ValueError(f"t must be a scalar or have one entry per utterance ({B}), got {tt.numel()}")
+        lengths = self._check_lengths(lengths if lengths is not None else lengths_from_mask(mask), B, T)
         lib, handle = self._ensure(mu_.device, lengths, T, [0.0, 1.0], "euler")
         v = torch.empty_like(mu_)
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        arr = (C.c_float * tt.numel())(*tt.tolist())
         N.check(lib, handle, lib.cfm_set_speakers(handle, spks_.data_ptr() if spks_ is not None else None))
-        N.check(lib, handle, lib.cfm_estimator(handle, x_.data_ptr(), mu_.data_ptr(), float(tt), v.data_ptr(), stream))
+        N.check(lib, handle, lib.cfm_estimator_t(handle, x_.data_ptr(), mu_.data_ptr(), arr, tt.numel(), v.data_ptr(), stream))
         return v
 
-    def compute_loss(self, x1, mask, mu):
-        raise NotImplementedError("training (reference flow_matching.py:65-107) is outside this build's scope: "
-                                  "the CUDA path is forward/inference only (DESIGN.md, 'out of scope')")
+    @torch.inference_mode()
+    def compute_loss(self, x1, mask, mu, t=None, x0=None):
+        """Forward value of the conditional-flow-matching loss (reference flow_matching.py:65-107): same draws (``t`` then the
+        prior noise, from the global generator of ``mu``'s device), same masked MSE; the estimator call with t of shape (B,)
+        runs on the CUDA path.  No autograd graph is built - this library has no backward, so the value
+        serves validation / monitoring, not optimisation.  ``t`` (B,) and ``x0`` can be injected for parity tests."""
+        b = mu.shape[0]
+        if t is None:
+            t = torch.rand([b, 1, 1], device=mu.device, dtype=mu.dtype)
+        t = t.reshape(b, 1, 1).to(device=mu.device, dtype=mu.dtype)
+        if x0 is None:
+            x0 = mu + torch.randn_like(x1) if self.use_mu_prior else torch.randn_like(x1)
+        y = (1 - (1 - self.sigma_min) * t) * x0 + t * x1
+        u = x1 - (1 - self.sigma_min) * x0
+        was_training = self.training
+        self.eval()  # dropout (p = 0.05 at two sites) is NOT applied: the value is the eval-mode loss
+        try:
+            pred = self._estimator_call(y, mask, mu, t.reshape(b))
+        finally:
+            self.train(was_training)
+        return torch.nn.functional.mse_loss(pred * mask, u * mask, reduction="sum") / (torch.sum(mask) * u.shape[1])
+
+    def timeline(self, x, t_span, mu, lengths):
+        """cfm_debug_timeline: in-situ time of every launch of one direct-launch decode -> list of (tag, M, N, K, flops, us)."""
+        mu_, x_ = self._prep(mu), self._prep(x)
+        B, F, T = self._check_shapes(mu_, x_)
+        lengths = self._check_lengths(lengths, B, T)
+        lib, handle = self._ensure(mu_.device, lengths, T, self._t_list(t_span), self.solver)
+        out = torch.empty_like(mu_)
+        buf = C.create_string_buffer(1 << 20)
+        stream = torch.cuda.current_stream(mu_.device).cuda_stream
+        N.check(lib, handle, lib.cfm_debug_timeline(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr(), buf, len(buf), stream))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            f = line.split(",")
+            rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), float(f[4]), float(f[5])))
+        return rows
 
     # ------------------------------------------------------------------ introspection (tests / bench)
     def plan_info(self):

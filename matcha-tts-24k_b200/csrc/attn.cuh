@@ -85,4 +85,11 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ qk
   }
 }
 
+// Instantiated in attn_simt_inst.cu (one object per variant: the unrolled head_dim loops are slow to compile); cfm.cu launches
+// through these getters and never names the template.
+KernelInfo kinfo_attn_simt_bf16_64();
+KernelInfo kinfo_attn_simt_bf16_32();
+KernelInfo kinfo_attn_simt_f32_64();
+KernelInfo kinfo_attn_simt_f32_32();
+
 }  // namespace cfm

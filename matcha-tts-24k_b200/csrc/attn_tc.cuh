@@ -69,6 +69,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
+#ifdef CFM_ATTN_KERNEL_TU  // the kernel body is compiled only in attn_inst.cu; cfm.cu launches through kinfo_attn_tc()
 __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int inner,
                const UttTable* __restrict__ utt, const int4* __restrict__ work, bf16* __restrict__ out, long long ldo,
@@ -310,8 +311,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   }
 }
 
+KernelInfo kinfo_attn_tc() { return KernelInfo{reinterpret_cast<const void*>(&attn_tc_kernel), AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES}; }
+#else
+
 inline int attn_tc_set_attr(std::string* err) {
-  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(kinfo_attn_tc().fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     *err = std::string("cudaFuncSetAttribute(attn_tc_kernel): ") + cudaGetErrorString(e);
     return -2;
@@ -344,13 +348,17 @@ inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_tc_kernel, tm_q, tm_kv, inner, utt, work, static_cast<bf16*>(out), ldo,
-                                     scale * 1.4426950408889634f, prof);
+  bf16* out_b = static_cast<bf16*>(out);
+  float scale_log2 = scale * 1.4426950408889634f;
+  void* args[] = {&tm_q, &tm_kv, &inner, &utt, &work, &out_b, &ldo, &scale_log2, &prof};
+  cudaError_t e = cudaLaunchKernelExC(&cfg, kinfo_attn_tc().fn, args);
   if (e != cudaSuccess) {
     *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);
     return -2;
   }
   return 0;
 }
+
+#endif  // CFM_ATTN_KERNEL_TU
 
 }  // namespace cfm

@@ -81,6 +81,12 @@ struct LaneDef {  // a contiguous group of utterances that runs as its own branc
 
 struct Plan {
   int B = 0, T = 0;
+  int solver = 0;
+  std::vector<float> t_span;   // with L, T, solver: the cache key (cfm_plan)
+  unsigned long long last_use = 0;
+  char* ws_base = nullptr;     // this plan's workspace block (from the handle's block pool)
+  size_t ws_cap = 0, ws_off = 0;
+  int n_trows = 0;             // rows of the time-embedding buffers: max(NFE, B) + 1 (per-utterance t of cfm_estimator_t)
   std::vector<LaneDef> lanes;
   std::vector<int> L;
   int M1 = 0, M2 = 0;
@@ -98,7 +104,7 @@ struct Plan {
   float *xstate = nullptr, *vout = nullptr, *kbuf[3] = {nullptr, nullptr, nullptr};
   double* stats = nullptr;
   size_t stats_bytes = 0;
-  float *stage_mu = nullptr, *stage_z = nullptr, *stage_out = nullptr;  // cfm_solve_host device staging
+  float *stage_mu = nullptr, *stage_z = nullptr, *stage_out = nullptr, *stage_spk = nullptr;  // cfm_solve_host device staging
   // activations per resolution (index 0 = full, 1 = half)
   void* xin = nullptr;
   int xin_ld = 0;
@@ -120,7 +126,19 @@ struct cfm_handle {
   std::vector<void*> wallocs;
   Model model;
   bool weights_loaded = false;
-  Plan* plan = nullptr;
+  Plan* plan = nullptr;           // current plan (one of `plans`)
+  std::vector<Plan*> plans;       // LRU cache of plans keyed by (lengths, T, t_span, solver): a server alternates between shapes
+  int plan_cache = 8;             // plans kept ("plan_cache" option)
+  unsigned long long use_clock = 0;
+  std::vector<std::pair<char*, size_t>> free_blocks;  // workspace blocks of evicted plans, reused by later plans
+  cudaEvent_t busy_event = nullptr;  // recorded after every enqueue; the next call's stream waits on it (one workspace per plan,
+  bool busy_valid = false;           // shared state in the handle: calls on different streams are ordered, never concurrent)
+  // debug timeline (cfm_debug_timeline): one event before every launch of a direct-launch decode
+  struct TlEntry { const char* tag; int M, N, K; double flops; cudaEvent_t ev; };
+  bool tl_on = false;
+  std::vector<TlEntry> tl;
+  size_t tl_n = 0;
+  const char* tag = "gemm";       // label of the next launch_gemm (set by the schedule code)
   EncodeTiledFn encode = nullptr;
   int sm_count = 148;
   int max_clusters[5] = {0, 148, 74, 0, 37};  // co-resident clusters of size 1, 2, 4 (queried at create)
@@ -156,9 +174,6 @@ struct cfm_handle {
   std::vector<cudaStream_t> lane_streams;
   std::vector<cudaEvent_t> lane_events;
   cudaEvent_t fork_event = nullptr;
-  // plan workspace arena: grown on demand, kept across cfm_plan calls (a server re-plans for every new batch shape)
-  char* ws_base = nullptr;
-  size_t ws_cap = 0, ws_off = 0;
   int C() const { return cfg.channels; }
   int inner() const { return cfg.n_heads * cfg.head_dim; }
 };
@@ -208,13 +223,13 @@ void free_arena(std::vector<void*>& arena) {
   arena.clear();
 }
 
-// Bump allocation from the handle's persistent workspace arena; falls back to cudaMalloc if the size estimate was short.
+// Bump allocation from the plan's workspace block; falls back to cudaMalloc if the size estimate was short.
 int plan_alloc(cfm_handle* h, Plan* pl, void** out, size_t bytes) {
   bytes = (bytes + 1023) / 1024 * 1024;
   if (bytes == 0) bytes = 1024;
-  if (h->ws_off + bytes <= h->ws_cap) {
-    *out = h->ws_base + h->ws_off;
-    h->ws_off += bytes;
+  if (pl->ws_off + bytes <= pl->ws_cap) {
+    *out = pl->ws_base + pl->ws_off;
+    pl->ws_off += bytes;
     pl->bytes += bytes;
     return 0;
   }
@@ -224,29 +239,73 @@ template <typename P>
 int plan_alloc_t(cfm_handle* h, Plan* pl, P** out, size_t count) {
   return plan_alloc(h, pl, reinterpret_cast<void**>(out), count * sizeof(P));
 }
-int ensure_workspace(cfm_handle* h, size_t need) {
-  if (need > h->ws_cap) {
-    if (h->ws_base) CK(cudaFree(h->ws_base));
-    h->ws_base = nullptr, h->ws_cap = 0;
+// Workspace block for a new plan: a block of an evicted plan if one fits (a server sees a new length with every request and
+// must not pay cudaMalloc / cudaFree, which synchronise the device), else a fresh allocation.  Cleared on `s`.
+int acquire_workspace(cfm_handle* h, Plan* pl, size_t need, cudaStream_t s) {
+  int best = -1;
+  for (int i = 0; i < (int)h->free_blocks.size(); ++i)
+    if (h->free_blocks[i].second >= need && (best < 0 || h->free_blocks[i].second < h->free_blocks[best].second)) best = i;
+  if (best >= 0 && h->free_blocks[best].second <= 4 * need + (64u << 20)) {
+    pl->ws_base = h->free_blocks[best].first, pl->ws_cap = h->free_blocks[best].second;
+    h->free_blocks.erase(h->free_blocks.begin() + best);
+  } else {
     const size_t cap = need + need / 8;
-    CK(cudaMalloc(reinterpret_cast<void**>(&h->ws_base), cap));
-    h->ws_cap = cap;
+    CK(cudaMalloc(reinterpret_cast<void**>(&pl->ws_base), cap));
+    pl->ws_cap = cap;
   }
   // Guard rows and padding columns are never written by the kernels and must read as zero (stale bytes of a previous
   // plan, reinterpreted as bf16, can be Inf/NaN and 0 * NaN poisons an MMA): clear what this plan will use (~0.1 ms/GB).
-  CK(cudaMemset(h->ws_base, 0, std::min(need, h->ws_cap)));
-  h->ws_off = 0;
+  CK(cudaMemsetAsync(pl->ws_base, 0, std::min(need, pl->ws_cap), s));
+  pl->ws_off = 0;
   return 0;
 }
 
-void free_plan(cfm_handle* h) {
-  h->win_bytes = 0;  // the L2 access-policy window points into the plan's workspace
-  if (!h->plan) return;
-  if (h->plan->exec) cudaGraphExecDestroy(h->plan->exec);
-  if (h->plan->graph) cudaGraphDestroy(h->plan->graph);
-  free_arena(h->plan->allocs);
-  delete h->plan;
+void free_plan(cfm_handle* h, Plan* pl, bool keep_block) {
+  if (!pl) return;
+  if (h->plan == pl) h->plan = nullptr, h->win_bytes = 0;  // the L2 access-policy window points into the plan's workspace
+  if (pl->exec) cudaGraphExecDestroy(pl->exec);
+  if (pl->graph) cudaGraphDestroy(pl->graph);
+  free_arena(pl->allocs);
+  if (pl->ws_base) {
+    if (keep_block && h->free_blocks.size() < 4) h->free_blocks.push_back({pl->ws_base, pl->ws_cap});
+    else cudaFree(pl->ws_base);
+  }
+  delete pl;
+}
+// Drops every cached plan (weights or kernel-selection options changed, handle destroyed).  Synchronises the device first:
+// the plans' buffers may still be in use.
+void free_all_plans(cfm_handle* h) {
+  if (!h->plans.empty() || !h->free_blocks.empty()) cudaDeviceSynchronize();
+  for (Plan* pl : h->plans) free_plan(h, pl, false);
+  h->plans.clear();
   h->plan = nullptr;
+  for (auto& b : h->free_blocks) cudaFree(b.first);
+  h->free_blocks.clear();
+}
+
+// Orders this call behind whatever the handle enqueued last, on any stream (the workspace is shared state).
+int enter_stream(cfm_handle* h, cudaStream_t s) {
+  if (h->busy_valid) CK(cudaStreamWaitEvent(s, h->busy_event, 0));
+  return 0;
+}
+int leave_stream(cfm_handle* h, cudaStream_t s) {
+  CK(cudaEventRecord(h->busy_event, s));
+  h->busy_valid = true;
+  return 0;
+}
+
+// Timeline mark: an event before the launch that follows (cfm_debug_timeline).
+int tl_mark(cfm_handle* h, cudaStream_t s, const char* tag, int M, int N, int K, double flops) {
+  if (!h->tl_on) return 0;
+  if (h->tl_n == h->tl.size()) {
+    cfm_handle::TlEntry e{};
+    CK(cudaEventCreate(&e.ev));
+    h->tl.push_back(e);
+  }
+  cfm_handle::TlEntry& e = h->tl[h->tl_n++];
+  e.tag = tag, e.M = M, e.N = N, e.K = K, e.flops = flops;
+  CK(cudaEventRecord(e.ev, s));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ weights
@@ -463,57 +522,104 @@ int launch_ex(cfm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   return 0;
 }
 
-template <int BN>
-int launch_tc_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                 const GemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN>;
+// Launch information of the tensor-core GEMM kernels (instantiated in gemm_inst.cu, one object each).
+KernelInfo tc_info(int bn, int epi_warps) {
+  if (bn == 256 && epi_warps == 12) return kinfo_tc_256_12();
+  switch (bn) {
+    case 64: return kinfo_tc_64_8();
+    case 128: return kinfo_tc_128_8();
+    case 160: return kinfo_tc_160_8();
+    case 192: return kinfo_tc_192_8();
+    default: return kinfo_tc_256_8();
+  }
+}
+KernelInfo tc2_info(int bn) {
+  switch (bn) {
+    case 128: return kinfo_tc2_128();
+    case 160: return kinfo_tc2_160();
+    case 192: return kinfo_tc2_192();
+    default: return kinfo_tc2_256();
+  }
+}
+
+// Same as launch_ex for a kernel known by address (the GEMM kernels all take (tmA0, tmA1, tmW, tmOut, params)).
+int launch_gemm_kernel(cfm_handle* h, const KernelInfo& k, int grid, cudaStream_t s, int cluster, const CUtensorMap& a0,
+                       const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o, const GemmParams& p) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(k.threads), cfg.dynamicSmemBytes = k.smem, cfg.stream = s;
+  cudaLaunchAttribute attr[3];
+  int n = 0;
+  if (h->win_bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = h->win_ptr;
+    attr[n].val.accessPolicyWindow.num_bytes = h->win_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (h->pdl_now) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&w),
+                  const_cast<CUtensorMap*>(&o), const_cast<GemmParams*>(&p)};
+  CK(cudaLaunchKernelExC(&cfg, k.fn, args));
+  return 0;
+}
+
+int launch_tc_bn(cfm_handle* h, int BN, int epi_warps, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                 const CUtensorMap& o, const GemmParams& p, cudaStream_t s) {
   const int CL = p.cluster;
   const int m_super = ((p.M + 127) / 128 + CL - 1) / CL;
   const int super_tiles = m_super * ((p.N + BN - 1) / BN);
   const int clusters = std::min(super_tiles, h->max_clusters[CL]);
-  return launch_ex(h, gemm_tc_kernel<BN>, dim3(clusters * CL), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, CL, a0, a1, w, o, p);
+  return launch_gemm_kernel(h, tc_info(BN, epi_warps), clusters * CL, s, CL, a0, a1, w, o, p);
 }
 
-// SnakeBeta GEMM (FF1) with 12 epilogue warps: its epilogue (one MUFU sine + 5 FP32 operations per element) is what bounds it.
-int launch_tc_snake12(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
-                      const GemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<256, 12>;
-  const int tiles = ((p.M + 127) / 128) * ((p.N + 255) / 256);
-  return launch_ex(h, gemm_tc_kernel<256, 12>, dim3(std::min(tiles, h->max_clusters[1])), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 1, a0, a1, w, o, p);
-}
-
-template <int BN>
-int launch_tc2_bn(cfm_handle* h, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
+int launch_tc2_bn(cfm_handle* h, int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& o,
                   const GemmParams& p, cudaStream_t s) {
-  using Cfg = Tc2Cfg<BN>;
   const int m_pairs = (p.M + 255) / 256;
   const int pair_tiles = m_pairs * ((p.N + BN - 1) / BN);
   const int pairs = std::min(pair_tiles, h->max_clusters[2]);
-  return launch_ex(h, gemm_tc2_kernel<BN>, dim3(pairs * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, 2, a0, a1, w, o, p);
+  return launch_gemm_kernel(h, tc2_info(BN), pairs * 2, s, 2, a0, a1, w, o, p);
 }
 
-template <int BN>
-int set_tc2_attr(cfm_handle* h) {
-  CK(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<BN>::SMEM_BYTES));
-  return 0;
-}
-
-template <int BN>
-int set_tc_attr(cfm_handle* h) {
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
-  if (BN == 192) {  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
-    for (int CL = 1; CL <= 4; CL *= 2) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof cfg);
-      cfg.gridDim = dim3(h->sm_count / CL * CL), cfg.blockDim = dim3(TcCfg<BN>::THREADS), cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr, cfg.numAttrs = 1;
-      int n = 0;
-      CK(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN>, &cfg));
-      h->max_clusters[CL] = std::max(1, n);
-    }
+int set_gemm_attrs(cfm_handle* h) {
+  const int bns[] = {64, 128, 160, 192, 256};
+  for (int bn : bns) {
+    const KernelInfo k = tc_info(bn, 8);
+    CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+  }
+  {
+    const KernelInfo k = tc_info(256, 12);
+    CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+  }
+  const int bns2[] = {128, 160, 192, 256};
+  for (int bn : bns2) {
+    const KernelInfo k = tc2_info(bn);
+    CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+  }
+  const KernelInfo k = tc_info(192, 8);  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
+  for (int CL = 1; CL <= 4; CL *= 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(h->sm_count / CL * CL), cfg.blockDim = dim3(k.threads), cfg.dynamicSmemBytes = k.smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    int n = 0;
+    CK(cudaOccupancyMaxActiveClusters(&n, k.fn, &cfg));
+    h->max_clusters[CL] = std::max(1, n);
   }
   return 0;
 }
@@ -522,6 +628,7 @@ int set_tc_attr(cfm_handle* h) {
 int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   if (h->stopped()) return 0;
   h->launch_counter++;
+  CKR(tl_mark(h, s, h->tag, p.M, p.N, p.K * p.n_taps, 2.0 * p.M * p.N * p.K * p.n_taps));
   const bool tc = h->bf && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
   if (!tc) {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
@@ -556,23 +663,9 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   p.pair = pair_ok && bn >= 128 ? 1 : 0;
   p.cluster = p.pair ? 1 : h->cluster;
   CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, p.pair ? bn / 2 : bn / p.cluster));
-  if (p.pair) {
-    switch (bn) {
-      case 128: return launch_tc2_bn<128>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-      case 160: return launch_tc2_bn<160>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-      case 192: return launch_tc2_bn<192>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-      default: return launch_tc2_bn<256>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-    }
-  }
-  if (bn == 256 && p.mode == EPI_SNAKE && h->snake_warps == 12 && p.cluster == 1 && !p.tma_epi && !p.direct_epi)
-    return launch_tc_snake12(h, tmA[0], tmA[1], tmW, tmO, p, s);
-  switch (bn) {
-    case 64: return launch_tc_bn<64>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-    case 128: return launch_tc_bn<128>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-    case 160: return launch_tc_bn<160>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-    case 192: return launch_tc_bn<192>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-    default: return launch_tc_bn<256>(h, tmA[0], tmA[1], tmW, tmO, p, s);
-  }
+  if (p.pair) return launch_tc2_bn(h, bn, tmA[0], tmA[1], tmW, tmO, p, s);
+  const bool snake12 = bn == 256 && p.mode == EPI_SNAKE && h->snake_warps == 12 && p.cluster == 1 && !p.tma_epi && !p.direct_epi;
+  return launch_tc_bn(h, bn, snake12 ? 12 : 8, tmA[0], tmA[1], tmW, tmO, p, s);
 }
 
 // Common part of a GEMM call: one A matrix, `w.n_taps` taps with the given row shifts / A column offsets.
@@ -644,10 +737,12 @@ int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const double* sta
 
 // `fuse_ln` != nullptr (block2 of a resnet followed by a transformer stack, C % 128 == 0): also emits LayerNorm(out) -> R.Xn.
 int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
-                 float* out_f32, void* out_act, long long ld_act, cudaStream_t s, const NormW* fuse_ln = nullptr) {
+                 float* out_f32, void* out_act, long long ld_act, cudaStream_t s, const NormW* fuse_ln = nullptr,
+                 long long addvec_stride = 0) {
   if (h->stopped()) return 0;
   h->launch_counter++;
   const int C = h->C();
+  CKR(tl_mark(h, s, fuse_ln ? "gn_apply_ln" : "gn_apply", R.M, C, 0, 0.0));
   const double* stats = pl->stats + (long long)site * pl->B * 16;
   if (fuse_ln) {
     if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, stats, resid, *fuse_ln, s);
@@ -657,10 +752,10 @@ int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int sit
   const int blocks = (int)((items + 255) / 256);
   if (h->bf)
     return launch_ex(h, gn_apply_kernel<bf16, false>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, resid, (long long)C,
                      out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
   return launch_ex(h, gn_apply_kernel<float, true>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                   (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, resid, (long long)C,
+                   (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, resid, (long long)C,
                    out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
 }
 
@@ -670,6 +765,7 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
   static const int shifts[3] = {-1, 0, 1};
   GemmParams p = gemm_base(R.M, A, lda, R.M, w, shifts, nullptr);
   p.mode = EPI_STATS;
+  h->tag = w.K >= 2 * h->C() ? "conv3_stats_2C" : (w.K == h->C() ? "conv3_stats_C" : "conv3_stats_in");
   p.out_f32 = R.hraw, p.ld_f32 = h->C();
   p.row_info = R.info;
   p.stats = pl->stats + (long long)site * pl->B * 16;
@@ -679,6 +775,7 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
   CKR(launch_gemm(h, p, true, s));
   if (!p.fused_stats && !h->stopped()) {
     h->launch_counter++;
+    CKR(tl_mark(h, s, "gn_stats", R.M, h->C(), 0, 0.0));
     const int items = R.M * 8;
     gn_stats_kernel<<<(items + 255) / 256, 256, 0, s>>>(R.hraw, h->C(), R.M, h->C(), h->C() / 8, R.info, p.stats);
     CK(cudaGetLastError());
@@ -706,6 +803,7 @@ int run_layernorm(cfm_handle* h, const Res& R, const NormW& ln, cudaStream_t s) 
   if (h->stopped()) return 0;
   h->launch_counter++;
   const int C = h->C();
+  CKR(tl_mark(h, s, "layernorm", R.M, C, 0, 0.0));
   if (C % 128 == 0 && C <= 512) {
     if (h->bf) return launch_ln_vec<bf16>(h, R, ln, s);
     return launch_ln_vec<float>(h, R, ln, s);
@@ -722,23 +820,30 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
   if (h->stopped()) return 0;
   h->launch_counter++;
   const int I = h->inner(), D = h->cfg.head_dim;
+  if (h->tl_on) {  // 4 (L + 1)^2 H d per utterance of the lane (QK^T and PV, pad token included)
+    double fl = 0.0;
+    const bool full = R.M_all == h->plan->M1;
+    for (int b = R.b0; b < R.b0 + R.nb; ++b) {
+      const double nk = (full ? h->plan->L[b] : (h->plan->L[b] + 1) / 2) + 1;
+      fl += 4.0 * nk * nk * I;
+    }
+    CKR(tl_mark(h, s, "attention", R.M, I, 0, fl));
+  }
   const float scale = 1.0f / sqrtf((float)D);
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
   if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl_now != 0);
-  if (h->bf) {
-    if (D == 64)
-      attn_simt_kernel<bf16, 64><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
-                                                          static_cast<bf16*>(R.ao_all), I, scale);
-    else
-      attn_simt_kernel<bf16, 32><<<R.n_work, 128, 0, s>>>(static_cast<const bf16*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
-                                                          static_cast<bf16*>(R.ao_all), I, scale);
-  } else {
-    if (D == 64)
-      attn_simt_kernel<float, 64><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
-                                                           static_cast<float*>(R.ao_all), I, scale);
-    else
-      attn_simt_kernel<float, 32><<<R.n_work, 128, 0, s>>>(static_cast<const float*>(R.qkv_all), 3LL * I, I, R.utt, R.work,
-                                                           static_cast<float*>(R.ao_all), I, scale);
+  {
+    const KernelInfo k = h->bf ? (D == 64 ? kinfo_attn_simt_bf16_64() : kinfo_attn_simt_bf16_32())
+                               : (D == 64 ? kinfo_attn_simt_f32_64() : kinfo_attn_simt_f32_32());
+    const void* qkv = R.qkv_all;
+    long long ld = 3LL * I, ldo = I;
+    int inner = I;
+    const UttTable* utt = R.utt;
+    const int4* work = R.work;
+    void* out = R.ao_all;
+    float sc = scale;
+    void* args[] = {&qkv, &ld, &inner, &utt, &work, &out, &ldo, &sc};
+    CK(cudaLaunchKernel(k.fn, dim3(R.n_work), dim3(k.threads), args, 0, s));
   }
   CK(cudaGetLastError());
   return 0;
@@ -746,16 +851,17 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
 
 // ResnetBlock1D (reference decoder.py:48-63) on masked input A (K columns) -> fp32 residual stream R.X.
 int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const void* A, long long lda, int& site,
-               const float* tproj, cudaStream_t s, const NormW* fuse_ln) {
+               const float* tproj, long long tproj_stride, cudaStream_t s, const NormW* fuse_ln) {
   const int C = h->C();
   CKR(run_conv_stats(h, pl, R, A, lda, w.conv1, site, s));
   {  // res_conv (1x1) on the same masked input -> fp32
     GemmParams p = gemm_base(R.M, A, lda, R.M, w.res, nullptr, nullptr);
     p.mode = EPI_STATS, p.fused_stats = 0;
     p.out_f32 = R.rres, p.ld_f32 = C;
+    h->tag = "res_conv";
     CKR(launch_gemm(h, p, true, s));
   }
-  CKR(run_gn_apply(h, pl, R, w.gn1, site, tproj, nullptr, nullptr, R.hact, C, s));
+  CKR(run_gn_apply(h, pl, R, w.gn1, site, tproj, nullptr, nullptr, R.hact, C, s, nullptr, tproj_stride));
   site++;
   CKR(run_conv_stats(h, pl, R, R.hact, C, w.conv2, site, s));
   CKR(run_gn_apply(h, pl, R, w.gn2, site, nullptr, R.rres, R.X, nullptr, 0, s, fuse_ln));
@@ -771,38 +877,42 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
   {
     GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.qkv, nullptr, nullptr);
     p.mode = EPI_STORE, p.out_act = R.qkv, p.ld_act = 3 * I;
+    h->tag = "qkv";
     CKR(launch_gemm(h, p, true, s));
   }
   CKR(run_attention(h, R, s));
   {
     GemmParams p = gemm_base(R.M, R.ao, I, R.M, w.out, nullptr, nullptr);
     p.mode = EPI_RESID, p.resid = R.X, p.ld_resid = C, p.out_f32 = R.X, p.ld_f32 = C;
+    h->tag = "out_proj";
     CKR(launch_gemm(h, p, true, s));
   }
   CKR(run_layernorm(h, R, w.ln3, s));
   {
     GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.ff1, nullptr, nullptr);
     p.mode = EPI_SNAKE, p.ea = w.ea, p.ib = w.ib, p.out_act = R.ffh, p.ld_act = 4 * C;
+    h->tag = "ff1_snake";
     CKR(launch_gemm(h, p, true, s));
   }
   {
     GemmParams p = gemm_base(R.M, R.ffh, 4 * C, R.M, w.ff2, nullptr, nullptr);
     p.mode = EPI_RESID, p.resid = R.X, p.ld_resid = C, p.out_f32 = R.X, p.ld_f32 = C;
     p.out_act = copy_dst, p.ld_act = copy_ld, p.row_info = R.info;
+    h->tag = copy_dst ? "ff2_copy" : "ff2";
     CKR(launch_gemm(h, p, true, s));
   }
   return 0;
 }
 
 int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void* A, long long lda, int& site,
-              const float* tproj, void* copy_dst, long long copy_ld, cudaStream_t s) {
+              const float* tproj, long long tproj_stride, void* copy_dst, long long copy_ld, cudaStream_t s) {
   if (h->l2_persist_mb > 0) {  // L2 access-policy window = this stage's fp32 residual stream (read / updated 6x per block)
     h->win_ptr = R.X;
     h->win_bytes = std::min((size_t)R.M * h->C() * sizeof(float), h->win_max);
   }
   // the resnet's last GroupNorm-apply also produces LayerNorm1 of the first transformer block when the width allows
   const bool fuse = h->C() % 128 == 0 && h->C() <= 512 && !w.blocks.empty() && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS);
-  CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, s, fuse ? &w.blocks[0].ln1 : nullptr));
+  CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, tproj_stride, s, fuse ? &w.blocks[0].ln1 : nullptr));
   for (size_t j = 0; j < w.blocks.size(); ++j) {
     const bool last = j + 1 == w.blocks.size();
     CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s, fuse && j == 0));
@@ -811,12 +921,15 @@ int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void
 }
 
 // One estimator evaluation of one lane + the ODE stage update fused in final_proj's epilogue.
-int emit_nfe(cfm_handle* h, Plan* pl, const LaneDef& ln, int nfe_index, const OdeStage& st, float* out_f32_override, cudaStream_t s) {
+// per_utt_t: the time-embedding rows are indexed by utterance (one t per sample) instead of by NFE.
+int emit_nfe(cfm_handle* h, Plan* pl, const LaneDef& ln, int nfe_index, const OdeStage& st, float* out_f32_override, cudaStream_t s,
+             bool per_utt_t = false) {
   const int C = h->C(), F = h->cfg.out_channels, es = h->es;
   const Model& m = h->model;
   Res R1 = res_of(h, pl, 0, ln), R2 = res_of(h, pl, 1, ln);
   const long long row0 = 2LL * ln.r2;  // first full-resolution row of the lane
   h->launch_counter++;
+  CKR(tl_mark(h, s, "memset_stats", 0, 0, 0, 0.0));
   {  // zero the lane's GroupNorm sums of every site: stats is [site][B][16] doubles
     const int n_sites = 2 * (4 + h->cfg.n_mid_blocks) + 1;
     CK(cudaMemset2DAsync(pl->stats + (long long)ln.b0 * 16, (size_t)pl->B * 16 * sizeof(double), 0, (size_t)ln.nb * 16 * sizeof(double),
@@ -825,52 +938,57 @@ int emit_nfe(cfm_handle* h, Plan* pl, const LaneDef& ln, int nfe_index, const Od
   int site = 0;
   int stage_i = 0;
   const int n_res = 4 + h->cfg.n_mid_blocks;
-  auto tproj = [&](int r) { return pl->tproj + ((long long)nfe_index * n_res + r) * C; };
+  auto tproj = [&](int r) { return pl->tproj + ((long long)(per_utt_t ? 0 : nfe_index) * n_res + r) * C; };
+  const long long tps = per_utt_t ? (long long)n_res * C : 0;
   void* xin = act_off(pl->xin, row0 * pl->xin_ld, es);
 
   // down 0 (full resolution): [x | mu] -> X1; masked copy of the stage output -> right half of cat1 (skip h0)
-  CKR(run_stage(h, pl, R1, m.stages[stage_i], xin, pl->xin_ld, site, tproj(stage_i), act_off(R1.cat, C, es), 2 * C, s));
+  CKR(run_stage(h, pl, R1, m.stages[stage_i], xin, pl->xin_ld, site, tproj(stage_i), tps, act_off(R1.cat, C, es), 2 * C, s));
   stage_i++;
   {  // Downsample1D: Conv1d k3 s2 p1 on the masked skip, rows viewed in pairs [M2, 4C]
     const int shifts[3] = {-1, 0, 0};
     const int acols[3] = {3 * C, C, 3 * C};
     GemmParams p = gemm_base(R2.M, R1.cat, 4LL * C, R2.M, m.down_s2, shifts, acols);
     p.mode = EPI_MASK, p.row_info = R2.info, p.out_act = R2.sin_, p.ld_act = C;
+    h->tag = "conv_s2";
     CKR(launch_gemm(h, p, true, s));
   }
   // down 1 (half resolution); masked copy -> right half of cat2 (skip h1)
-  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), act_off(R2.cat, C, es), 2 * C, s));
+  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), tps, act_off(R2.cat, C, es), 2 * C, s));
   stage_i++;
   {  // stage-final Conv1d k3 on the masked skip
     const int shifts[3] = {-1, 0, 1};
     const int acols[3] = {C, C, C};
     GemmParams p = gemm_base(R2.M, R2.cat, 2LL * C, R2.M, m.down_tail, shifts, acols);
     p.mode = EPI_MASK, p.row_info = R2.info, p.out_act = R2.sin_, p.ld_act = C;
+    h->tag = "conv3_tail";
     CKR(launch_gemm(h, p, true, s));
   }
   for (int i = 0; i < h->cfg.n_mid_blocks; ++i) {
     const bool last = i + 1 == h->cfg.n_mid_blocks;
     void* dst = last ? R2.cat : R2.sin_;  // last mid block feeds the left half of cat2
-    CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), dst, last ? 2 * C : C, s));
+    CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.sin_, C, site, tproj(stage_i), tps, dst, last ? 2 * C : C, s));
     stage_i++;
   }
   // up 0 (half resolution) on [x | h1]
-  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.cat, 2 * C, site, tproj(stage_i), R2.sin_, C, s));
+  CKR(run_stage(h, pl, R2, m.stages[stage_i], R2.cat, 2 * C, site, tproj(stage_i), tps, R2.sin_, C, s));
   stage_i++;
   for (int phase = 0; phase < 2; ++phase) {  // ConvTranspose1d k4 s2 p1 as two interleaved 2-tap GEMMs
     const int sh_even[2] = {-1, 0}, sh_odd[2] = {0, 1};
     GemmParams p = gemm_base(R2.M, R2.sin_, C, R2.M, phase == 0 ? m.up_even : m.up_odd, phase == 0 ? sh_even : sh_odd, nullptr);
     p.mode = EPI_MASK, p.row_info = R1.info, p.row_mul = 2, p.row_add = phase;
     p.out_act = act_off(R1.cat, (long long)phase * 2 * C, es), p.ld_act = 4 * C;
+    h->tag = "conv_transpose";
     CKR(launch_gemm(h, p, true, s));
   }
   // up 1 (full resolution) on [x | h0]
-  CKR(run_stage(h, pl, R1, m.stages[stage_i], R1.cat, 2 * C, site, tproj(stage_i), R1.sin_, C, s));
+  CKR(run_stage(h, pl, R1, m.stages[stage_i], R1.cat, 2 * C, site, tproj(stage_i), tps, R1.sin_, C, s));
   stage_i++;
   {  // stage-final Conv1d k3
     const int shifts[3] = {-1, 0, 1};
     GemmParams p = gemm_base(R1.M, R1.sin_, C, R1.M, m.up_tail, shifts, nullptr);
     p.mode = EPI_MASK, p.row_info = R1.info, p.out_act = R1.hact, p.ld_act = C;
+    h->tag = "conv3_tail";
     CKR(launch_gemm(h, p, true, s));
   }
   // final Block1D + 1x1 projection with the ODE update in the epilogue
@@ -894,6 +1012,7 @@ int emit_nfe(cfm_handle* h, Plan* pl, const LaneDef& ln, int nfe_index, const Od
       p.out_f32 = st.write_state ? pl->xstate + row0 * F : nullptr, p.ld_f32 = F;
       p.out_act = xin, p.ld_act = pl->xin_ld;
     }
+    h->tag = "final_proj_ode";
     CKR(launch_gemm(h, p, true, s));
   }
   return 0;
@@ -906,6 +1025,7 @@ int emit_time_embedding(cfm_handle* h, Plan* pl, int n_t, const float* t_dev, cu
   auto gemv = [&](const float* x, long long ldx, const float* W, int N, int K, const float* b, int ai, int ao, float* y,
                   long long ldy) -> int {
     h->launch_counter++;
+    CKR(tl_mark(h, s, "time_mlp", n_t, N, K, 2.0 * n_t * N * K));
     const long long warps = (long long)n_t * N;
     gemv_rows_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, s>>>(x, ldx, n_t, W, N, K, b, ai, ao, y, ldy);
     CK(cudaGetLastError());
@@ -1118,23 +1238,12 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
     return bail(CFM_ERR_CUDA);
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  int r = 0;
-  r = r ? r : set_tc_attr<64>(h);
-  r = r ? r : set_tc_attr<128>(h);
-  r = r ? r : set_tc_attr<160>(h);
-  r = r ? r : set_tc_attr<192>(h);
-  r = r ? r : set_tc_attr<256>(h);
-  if (!r && cudaFuncSetAttribute(gemm_tc_kernel<256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, 12>::SMEM_BYTES) != cudaSuccess) {
-    h->err = "cudaFuncSetAttribute(gemm_tc_kernel<256, 12>) failed";
-    r = CFM_ERR_CUDA;
-  }
-  r = r ? r : set_tc2_attr<128>(h);
-  r = r ? r : set_tc2_attr<160>(h);
-  r = r ? r : set_tc2_attr<192>(h);
-  r = r ? r : set_tc2_attr<256>(h);
+  int r = set_gemm_attrs(h);
   r = r ? r : attn_tc_set_attr(&h->err);
   if (r) return bail(r);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }
+  if (cudaEventCreateWithFlags(&h->busy_event, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(CFM_ERR_CUDA); }
+  if (const char* e = getenv("CFM_B200_PLAN_CACHE")) h->plan_cache = std::max(1, atoi(e));
   if (const char* e = getenv("CFM_B200_L2_PERSIST_MB")) h->l2_persist_mb = std::max(0, atoi(e));
   if (apply_l2_persist(h, h->l2_persist_mb) != 0) return bail(CFM_ERR_CUDA);
   *out = h;
@@ -1145,9 +1254,10 @@ void cfm_destroy(cfm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  free_plan(h);
+  free_all_plans(h);
   free_arena(h->wallocs);
-  if (h->ws_base) cudaFree(h->ws_base);
+  for (auto& e : h->tl) cudaEventDestroy(e.ev);
+  if (h->busy_event) cudaEventDestroy(h->busy_event);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (cudaStream_t st : h->lane_streams) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->lane_events) cudaEventDestroy(ev);
@@ -1159,7 +1269,7 @@ int cfm_load_weights(cfm_handle* h, const cfm_weight_desc* descs, int32_t n) {
   if (!h || !descs || n <= 0) return fail(h, CFM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  free_plan(h);  // the captured graph references the old weight buffers
+  free_all_plans(h);  // the captured graphs reference the old weight buffers
   free_arena(h->wallocs);
   h->model = Model();
   h->weights_loaded = false;
@@ -1220,14 +1330,43 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   if (n_points < 2) return fail(h, CFM_ERR_INVALID, "t_span needs at least 2 points");
   for (int b = 0; b < batch; ++b)
     if (lengths[b] < 1 || lengths[b] > t_pad) return fail(h, CFM_ERR_INVALID, "lengths[%d]=%d outside [1, t_pad=%d]", b, lengths[b], t_pad);
+  if (solver < CFM_SOLVER_EULER || solver > CFM_SOLVER_RK4)
+    return fail(h, CFM_ERR_INVALID, "unknown solver id %d (expected euler=0, midpoint=1, heun3=2, rk4=3)", solver);
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaDeviceSynchronize());
-  free_plan(h);
+  // ---- plan cache: a TTS server alternates between a handful of shapes; re-planning (tables, workspace, graph) for a shape
+  // seen before is wasted work (reference server.py:93-119 decodes one request after the other through the same model).
+  h->use_clock++;
+  for (Plan* c : h->plans) {
+    if (c->B == batch && c->T == t_pad && c->solver == solver && (int)c->t_span.size() == n_points &&
+        memcmp(c->L.data(), lengths, sizeof(int) * batch) == 0 && memcmp(c->t_span.data(), t_span, sizeof(float) * n_points) == 0) {
+      c->last_use = h->use_clock;
+      h->plan = c;
+      h->pdl_now = h->pdl < 0 ? (c->M1 <= 2048 ? 1 : 0) : h->pdl;
+      return 0;
+    }
+  }
+  while ((int)h->plans.size() >= std::max(1, h->plan_cache)) {  // evict the least recently used plan; its block is reused below
+    size_t lru = 0;
+    for (size_t i = 1; i < h->plans.size(); ++i)
+      if (h->plans[i]->last_use < h->plans[lru]->last_use) lru = i;
+    Plan* victim = h->plans[lru];
+    h->plans.erase(h->plans.begin() + lru);
+    // Nothing is freed here (no device synchronisation): the block goes to the pool, and whoever takes it next is ordered
+    // behind the victim's last kernels through the busy event.  A block that does not fit the pool is released by cudaFree,
+    // which waits for the device by itself.
+    free_plan(h, victim, true);
+  }
   Plan* pl = new Plan();
-  h->plan = pl;
-  pl->B = batch, pl->T = t_pad;
+  pl->B = batch, pl->T = t_pad, pl->solver = solver, pl->last_use = h->use_clock;
   pl->L.assign(lengths, lengths + batch);
+  pl->t_span.assign(t_span, t_span + n_points);
+  struct Guard {  // a failed plan is neither cached nor current
+    cfm_handle* h; Plan* pl; bool ok = false;
+    ~Guard() { if (!ok) free_plan(h, pl, false); }
+  } guard{h, pl};
   CKR(build_stages(h, pl, t_span, n_points, solver));
+  cudaStream_t ps = h->own_stream;  // set-up stream: ordered behind earlier work of the handle, later calls wait for it
+  CKR(enter_stream(h, ps));
 
   // ---- packed row tables (DESIGN.md "data layout"): a half-res segment is L2 valid rows + the halo / pad-token row +
   // one zero guard row (the halo row's k=3 conv reads row L2+1, which must not be the next utterance); full-res = 2x that.
@@ -1305,22 +1444,25 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     }
     if (!h->fork_event) CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
   }
-  {  // size the persistent workspace arena for this plan (tables + state + activations + host-path staging)
+  const int n_t = (int)pl->stages.size(), n_res = 4 + h->cfg.n_mid_blocks;
+  pl->n_trows = std::max(n_t, (int)batch) + 1;
+  {  // size this plan's workspace block (tables + state + activations + host-path staging)
     const size_t C_ = h->C(), I_ = h->inner(), F_ = h->cfg.out_channels, es_ = h->es, M1_ = pl->M1, M2_ = pl->M2;
-    const size_t nt = pl->stages.size(), nres = 4 + h->cfg.n_mid_blocks;
+    const size_t nt = pl->n_trows, nres = n_res;
     size_t need = (size_t)batch * 2 * sizeof(UttTable) + (M1_ + M2_) * 4 + (w1.size() + w2.size()) * sizeof(int4);
     need += nt * (4 + (size_t)h->cfg.in_channels * 4 + 2 * 4 * C_ * 4 + nres * C_ * 4);
     need += 5 * M1_ * F_ * 4 + (2 * nres + 1) * (size_t)batch * (16 * 8 + 8 * 8);
     need += M1_ * (size_t)roundup(h->cfg.in_channels, 64) * es_;
     need += (M1_ + M2_) * (3 * C_ * 4 + (5 * C_ + 4 * I_ + 4 * C_) * es_);
-    need += 3 * (size_t)batch * F_ * t_pad * 4;
+    need += 3 * (size_t)batch * F_ * t_pad * 4 + (size_t)batch * std::max(h->cfg.in_channels - 2 * h->cfg.out_channels, 1) * 4;
     need += 64 * 1024 + (1 << 20);  // per-allocation 1 KB rounding, slack
-    CKR(ensure_workspace(h, need));
+    CKR(acquire_workspace(h, pl, need, ps));
   }
   auto up = [&](auto** dst, const auto& vec) -> int {
     using E = typename std::remove_reference<decltype(vec[0])>::type;
     CKR(plan_alloc(h, pl, reinterpret_cast<void**>(dst), vec.size() * sizeof(E)));
-    CK(cudaMemcpy(*dst, vec.data(), vec.size() * sizeof(E), cudaMemcpyHostToDevice));
+    // pageable source: the runtime stages the bytes before returning, so the vectors may go out of scope
+    CK(cudaMemcpyAsync(*dst, vec.data(), vec.size() * sizeof(E), cudaMemcpyHostToDevice, ps));
     return 0;
   };
   CKR(up(&pl->utt1, u1));
@@ -1332,14 +1474,13 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
 
   // ---- workspace
   const int C = h->C(), I = h->inner(), F = h->cfg.out_channels, es = h->es, T4 = 4 * C;
-  const int n_t = (int)pl->stages.size(), n_res = 4 + h->cfg.n_mid_blocks;
-  std::vector<float> tv(n_t);
+  std::vector<float> tv(pl->n_trows, 0.f);
   for (int j = 0; j < n_t; ++j) tv[j] = pl->stages[j].t;
   CKR(up(&pl->tvals, tv));
-  CKR(plan_alloc_t(h, pl, &pl->sinemb, (size_t)n_t * h->cfg.in_channels));
-  CKR(plan_alloc_t(h, pl, &pl->temb_a, (size_t)n_t * T4));
-  CKR(plan_alloc_t(h, pl, &pl->temb, (size_t)n_t * T4));
-  CKR(plan_alloc_t(h, pl, &pl->tproj, (size_t)n_t * n_res * C));
+  CKR(plan_alloc_t(h, pl, &pl->sinemb, (size_t)pl->n_trows * h->cfg.in_channels));
+  CKR(plan_alloc_t(h, pl, &pl->temb_a, (size_t)pl->n_trows * T4));
+  CKR(plan_alloc_t(h, pl, &pl->temb, (size_t)pl->n_trows * T4));
+  CKR(plan_alloc_t(h, pl, &pl->tproj, (size_t)pl->n_trows * n_res * C));
   CKR(plan_alloc_t(h, pl, &pl->xstate, (size_t)pl->M1 * F));
   CKR(plan_alloc_t(h, pl, &pl->vout, (size_t)pl->M1 * F));
   int n_k = 0;
@@ -1363,13 +1504,16 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     CKR(plan_alloc(h, pl, &pl->sin_[r], M * C * es));
     CKR(plan_alloc(h, pl, &pl->cat[r], M * 2 * C * es));
   }
-  CK(cudaDeviceSynchronize());
+  CKR(leave_stream(h, ps));  // tables and the cleared workspace are ready before any later call touches them
 
   // ---- the whole ODE loop as one CUDA graph: captured here, or lazily before the plan's (graph_after + 1)-th decode.
   // Capturing and instantiating ~1200 nodes costs more than a B = 1 decode itself, and a server sees a new length with
   // almost every request, so a plan's first decode uses direct launches and the graph is built only when the plan is reused.
   h->launch_counter = 0;
   pl->solves = 0;
+  h->plan = pl;
+  h->plans.push_back(pl);
+  guard.ok = true;
   if (h->graph_after == 0) CKR(capture_graph(h, pl));
   return 0;
 }
@@ -1383,6 +1527,7 @@ int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* 
   h->launch_counter = 0;
   if (!pl->exec && pl->solves >= h->graph_after) CKR(capture_graph(h, pl));
   pl->solves++;
+  CKR(enter_stream(h, s));
   CKR(emit_pack(h, pl, z, mu, s));
   if (pl->exec) {
     CK(cudaGraphLaunch(pl->exec, s));
@@ -1391,49 +1536,112 @@ int cfm_solve(cfm_handle* h, const float* mu, const float* z, float* out, void* 
     pl->launches_per_solve = h->launch_counter + 1;
   }
   CKR(emit_unpack(h, pl, pl->xstate, z, out, s));
+  CKR(leave_stream(h, s));
   return 0;
 }
 
-int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) {
+static int solve_host_impl(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out) {
   if (!h || !mu || !z || !out) return fail(h, CFM_ERR_INVALID, "null argument");
   if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_solve_host before cfm_plan");
   Plan* pl = h->plan;
   CK(cudaSetDevice(h->cfg.device));
+  const int S = h->cfg.in_channels - 2 * h->cfg.out_channels;
+  if ((S > 0) != (spks != nullptr))
+    return fail(h, CFM_ERR_INVALID, "this estimator has %d speaker channels: %s", S,
+                S > 0 ? "use cfm_solve_host_spks with a host (batch, S) matrix" : "spks must be NULL");
   const size_t n = (size_t)pl->B * h->cfg.out_channels * pl->T;
+  cudaStream_t s = h->own_stream;
+  CKR(enter_stream(h, s));
   if (!pl->stage_mu) {  // device staging buffers live with the plan: no allocation on the per-call path
     CKR(plan_alloc_t(h, pl, &pl->stage_mu, n));
     CKR(plan_alloc_t(h, pl, &pl->stage_z, n));
     CKR(plan_alloc_t(h, pl, &pl->stage_out, n));
+    if (S > 0) CKR(plan_alloc_t(h, pl, &pl->stage_spk, (size_t)pl->B * S));
   }
-  CK(cudaMemcpyAsync(pl->stage_mu, mu, n * 4, cudaMemcpyHostToDevice, h->own_stream));
-  CK(cudaMemcpyAsync(pl->stage_z, z, n * 4, cudaMemcpyHostToDevice, h->own_stream));
-  CKR(cfm_solve(h, pl->stage_mu, pl->stage_z, pl->stage_out, h->own_stream));
-  CK(cudaMemcpyAsync(out, pl->stage_out, n * 4, cudaMemcpyDeviceToHost, h->own_stream));
-  CK(cudaStreamSynchronize(h->own_stream));
+  CK(cudaMemcpyAsync(pl->stage_mu, mu, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(pl->stage_z, z, n * 4, cudaMemcpyHostToDevice, s));
+  if (S > 0) CK(cudaMemcpyAsync(pl->stage_spk, spks, (size_t)pl->B * S * 4, cudaMemcpyHostToDevice, s));
+  h->spks = S > 0 ? pl->stage_spk : nullptr;  // never a pointer left over from an earlier device-side call
+  CKR(cfm_solve(h, pl->stage_mu, pl->stage_z, pl->stage_out, s));
+  h->spks = nullptr;
+  CK(cudaMemcpyAsync(out, pl->stage_out, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) { return solve_host_impl(h, mu, z, nullptr, out); }
+
+int cfm_solve_host_spks(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out) {
+  if (!spks) return fail(h, CFM_ERR_INVALID, "null argument");
+  return solve_host_impl(h, mu, z, spks, out);
+}
+
+int cfm_estimator_t(cfm_handle* h, const float* x, const float* mu, const float* t_host, int32_t n_t, float* v, void* stream) {
+  if (!h || !x || !mu || !v || !t_host) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_estimator before cfm_plan");
+  Plan* pl = h->plan;
+  if (n_t != 1 && n_t != pl->B) return fail(h, CFM_ERR_INVALID, "n_t must be 1 (one time for the batch) or the planned batch %d, got %d", pl->B, n_t);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(h->cfg.device));
+  CKR(enter_stream(h, s));
+  CKR(emit_pack(h, pl, x, mu, s));
+  // The time values go to the rows behind the planned grid (which stays intact for later solves).  Pageable source: staged by
+  // the runtime before the call returns, so the caller's array may be a temporary and no stream synchronisation is needed.
+  const int n_grid = (int)pl->stages.size();
+  float* t_dev = pl->tvals + (n_t == 1 ? pl->n_trows - 1 : 0);
+  std::vector<float> keep;
+  if (n_t != 1) {  // B time points overwrite the planned grid's slots: restore them afterwards
+    keep.resize(pl->n_trows, 0.f);
+    for (int j = 0; j < n_grid; ++j) keep[j] = pl->stages[j].t;
+  }
+  CK(cudaMemcpyAsync(t_dev, t_host, sizeof(float) * n_t, cudaMemcpyHostToDevice, s));
+  CKR(emit_time_embedding(h, pl, n_t, t_dev, s));
+  OdeStage st;
+  st.t = t_host[0], st.c_v = 1.f, st.kout = -1, st.write_state = false;
+  for (int j = 0; j < 3; ++j) st.c_k[j] = 0.f, st.kin[j] = -1;
+  h->launch_counter = 0;
+  const bool per_utt = n_t != 1;
+  CKR(for_each_lane(h, pl, s, [&](const LaneDef& ln, cudaStream_t ls) -> int { return emit_nfe(h, pl, ln, 0, st, pl->vout, ls, per_utt); }));
+  CKR(emit_unpack(h, pl, pl->vout, nullptr, v, s));
+  if (n_t != 1) CK(cudaMemcpyAsync(pl->tvals, keep.data(), sizeof(float) * pl->n_trows, cudaMemcpyHostToDevice, s));
+  CKR(leave_stream(h, s));
   return 0;
 }
 
 int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream) {
-  if (!h || !x || !mu || !v) return fail(h, CFM_ERR_INVALID, "null argument");
-  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_estimator before cfm_plan");
+  return cfm_estimator_t(h, x, mu, &t, 1, v, stream);
+}
+
+// Debug / measurement: one decode with direct launches and a CUDA event before every launch; writes "tag,M,N,K,flops,us" lines
+// (one per launch, in order; us = time to the next mark) into buf.  In-situ (warm-cache, back-to-back) per-kernel times: the
+// ncu launch lists in profiles/ are cold-cache and serialised.
+int cfm_debug_timeline(cfm_handle* h, const float* mu, const float* z, float* out, char* buf, int64_t cap, void* stream) {
+  if (!h || !mu || !z || !out || !buf || cap < 64) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_debug_timeline before cfm_plan");
   Plan* pl = h->plan;
+  if (pl->lanes.size() != 1) return fail(h, CFM_ERR_STATE, "cfm_debug_timeline needs a single-lane plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(h->cfg.device));
-  CKR(emit_pack(h, pl, x, mu, s));
-  CK(cudaMemcpyAsync(pl->tvals, &t, sizeof(float), cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // `t` lives on this call's stack
-  CKR(emit_time_embedding(h, pl, 1, pl->tvals, s));
-  OdeStage st;
-  st.t = t, st.c_v = 1.f, st.kout = -1, st.write_state = false;
-  for (int j = 0; j < 3; ++j) st.c_k[j] = 0.f, st.kin[j] = -1;
-  h->launch_counter = 0;
-  CKR(for_each_lane(h, pl, s, [&](const LaneDef& ln, cudaStream_t ls) -> int { return emit_nfe(h, pl, ln, 0, st, pl->vout, ls); }));
-  CKR(emit_unpack(h, pl, pl->vout, nullptr, v, s));
-  // restore the planned time grid for subsequent solves
-  std::vector<float> tv(pl->stages.size());
-  for (size_t j = 0; j < tv.size(); ++j) tv[j] = pl->stages[j].t;
+  CKR(enter_stream(h, s));
+  CKR(emit_pack(h, pl, z, mu, s));
+  h->tl_on = true, h->tl_n = 0;
+  int r = emit_ode_loop(h, pl, s);
+  if (r == 0) r = tl_mark(h, s, "end", 0, 0, 0, 0.0);
+  h->tl_on = false;
+  CKR(r);
+  CKR(emit_unpack(h, pl, pl->xstate, z, out, s));
+  CKR(leave_stream(h, s));
   CK(cudaStreamSynchronize(s));
-  CK(cudaMemcpy(pl->tvals, tv.data(), tv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  int64_t off = 0;
+  for (size_t i = 0; i + 1 < h->tl_n; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->tl[i].ev, h->tl[i + 1].ev));
+    const int w = snprintf(buf + off, (size_t)(cap - off), "%s,%d,%d,%d,%.6g,%.3f\n", h->tl[i].tag, h->tl[i].M, h->tl[i].N, h->tl[i].K,
+                           h->tl[i].flops, ms * 1e3);
+    if (w < 0 || off + w >= cap) return fail(h, CFM_ERR_INVALID, "timeline buffer too small (%lld bytes)", (long long)cap);
+    off += w;
+  }
+  buf[off] = 0;
   return 0;
 }
 
@@ -1513,11 +1721,18 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows) {
   if (!h || lanes < 1 || lanes > 16) return fail(h, CFM_ERR_INVALID, "lanes must be in [1, 16]");
   h->lanes_req = lanes;
   if (min_rows > 0) h->lane_min_rows = min_rows;
+  free_all_plans(h);  // cached plans were cut with the old lane count
   return 0;
 }
 
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   if (!h || !key) return fail(h, CFM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (strcmp(key, "plan_cache") == 0 && value >= 1) {
+    h->plan_cache = value;
+    return 0;
+  }
+  free_all_plans(h);  // kernel selection is baked into the cached plans' graphs
   if (strcmp(key, "tma_epi") == 0) h->tma_epi = value == 1 ? 0x3f : value;
   else if (strcmp(key, "pair_mode") == 0 && value >= 0 && value <= 2) h->pair_mode = value;
   else if (strcmp(key, "small_tiles") == 0 && value >= 0) h->small_tiles = value;

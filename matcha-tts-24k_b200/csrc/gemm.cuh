@@ -1333,4 +1333,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
+// The heavy kernels are instantiated in their own translation units (csrc/gemm_inst.cu / attn_inst.cu, one nvcc process per
+// instantiation, see build.py).  cfm.cu never names the kernel templates: it launches through the function pointers these
+// getters return (cudaLaunchKernelExC), so its own compilation does not instantiate them again.
+struct KernelInfo {
+  const void* fn;
+  int threads;
+  int smem;
+};
+#define CFM_FOR_EACH_TC(X) X(64, 8) X(128, 8) X(160, 8) X(192, 8) X(256, 8) X(256, 12)
+#define CFM_FOR_EACH_TC2(X) X(128) X(160) X(192) X(256)
+#define CFM_X_TC(BN, NEW) KernelInfo kinfo_tc_##BN##_##NEW();
+#define CFM_X_TC2(BN) KernelInfo kinfo_tc2_##BN();
+CFM_FOR_EACH_TC(CFM_X_TC)
+CFM_FOR_EACH_TC2(CFM_X_TC2)
+#undef CFM_X_TC
+#undef CFM_X_TC2
+KernelInfo kinfo_attn_tc();
+
 }  // namespace cfm

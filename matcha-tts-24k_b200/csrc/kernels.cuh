@@ -84,7 +84,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int F, int Tpad,
 
 // token-major fp32 state -> (B, F, T); frames t >= L take `fill` (the injected noise z for a solve, because the
 // masked velocity never moves padded frames; nullptr -> 0 for a bare estimator call).
-__global__ void unpack_rows_kernel(const float* __restrict__ state, long long ld, const UttTable* __restrict__ utt, int F,
+static __global__ void unpack_rows_kernel(const float* __restrict__ state, long long ld, const UttTable* __restrict__ utt, int F,
                                    int Tpad, const float* __restrict__ fill, float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -122,7 +122,7 @@ __global__ void pack_speaker_kernel(const float* __restrict__ spks, int S, const
 
 // ---------------------------------------------------------------------------------- GroupNorm
 // Stand-alone statistics pass (fp32 mode and the debug path; the tensor-core GEMM fuses this into its epilogue).
-__global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M, int C, int group_ch,
+static __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M, int C, int group_ch,
                                 const int* __restrict__ row_info, double* __restrict__ stats) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row, group)
   const int m = idx >> 3, g = idx & 7;
@@ -145,7 +145,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M
 // sums = epilogue sums + bias_rows * (sum_c b_c, sum_c b_c^2) for the padded frames that are never materialised
 // (DESIGN.md "pad-aware packing"), over group_ch * t_res elements (reference decoder.py:35-45 normalises over the
 // PADDED length).
-__global__ void gn_finalize_kernel(const double* __restrict__ stats, const double* __restrict__ bias_gsum,
+static __global__ void gn_finalize_kernel(const double* __restrict__ stats, const double* __restrict__ bias_gsum,
                                    const UttTable* __restrict__ utt, int n_utt, int group_ch, float2* __restrict__ mr) {
   ptx::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,8 +166,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
                                 const int* __restrict__ row_info, const double* __restrict__ stats,
                                 const double* __restrict__ bias_gsum, const UttTable* __restrict__ utt,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ addvec, const float* __restrict__ resid, long long ld_resid,
-                                float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act, long long ld_act) {
+                                const float* __restrict__ addvec, long long addvec_utt_stride, const float* __restrict__ resid,
+                                long long ld_resid, float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act,
+                                long long ld_act) {
+  // addvec: time-embedding projection added after Mish (reference decoder.py:60); one vector for the batch (stride 0) or one
+  // per utterance (stride > 0: per-sample t of the training forward, reference flow_matching.py:84-97)
   ptx::pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = C >> 3;
@@ -201,7 +204,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
       y[i] = PRECISE ? mish_precise(z) : mish_f(z);
     }
     if (addvec) {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addvec + c)), a1 = __ldg(reinterpret_cast<const float4*>(addvec + c + 4));
+      const float* av = addvec + (long long)b * addvec_utt_stride;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + c)), a1 = __ldg(reinterpret_cast<const float4*>(av + c + 4));
       y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w, y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
     }
   }
@@ -304,7 +308,7 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
 }
 
 // per-GroupNorm-site sums of the conv bias per group: [8][2] doubles (sum b, sum b^2)
-__global__ void bias_group_sums_kernel(const float* __restrict__ bias, int C, int group_ch, double* __restrict__ out) {
+static __global__ void bias_group_sums_kernel(const float* __restrict__ bias, int C, int group_ch, double* __restrict__ out) {
   const int g = threadIdx.x;
   if (g >= 8) return;
   double s = 0, ss = 0;
@@ -408,7 +412,7 @@ __global__ void layernorm_vec_kernel(const float* __restrict__ x, long long ldx,
 // Sinusoidal features (reference decoder.py:20-29) for NT time points: [NT][dim] = [sin | cos](1000 t f_k),
 // f_k = exp(-k ln(1e4)/(half-1)).  The reference evaluates this in fp32; each fp32 rounding step is reproduced,
 // with the transcendental functions taken in double and rounded once.
-__global__ void sinusoid_kernel(const float* __restrict__ t, int NT, int dim, float* __restrict__ out) {
+static __global__ void sinusoid_kernel(const float* __restrict__ t, int NT, int dim, float* __restrict__ out) {
   const int i = blockIdx.x, k = threadIdx.x;
   const int half = dim / 2;
   if (i >= NT || k >= half) return;
@@ -423,7 +427,7 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int NT, int dim, fl
 
 enum GemvAct : int { ACT_NONE = 0, ACT_SILU = 1, ACT_MISH = 2 };
 // y[i][n] = act_out(bias[n] + sum_k W[n][k] * act_in(x[i][k]));  one warp per (i, n); fp32 weights.
-__global__ void gemv_rows_kernel(const float* __restrict__ x, long long ldx, int NT, const float* __restrict__ W, int N,
+static __global__ void gemv_rows_kernel(const float* __restrict__ x, long long ldx, int NT, const float* __restrict__ W, int N,
                                  int K, const float* __restrict__ bias, int act_in, int act_out, float* __restrict__ y,
                                  long long ldy) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -462,7 +466,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, long long s_n,
   ActIO<T>::st(dst + ((long long)tap * n_stride + n) * ldd + k, v);
 }
 
-__global__ void snake_consts_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, int N,
+static __global__ void snake_consts_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, int N,
                                     float* __restrict__ ea, float* __restrict__ ib) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;

@@ -1,0 +1,146 @@
+"""GPU tests of the round-2 host-facing features, all through the C ABI and against the CPU oracle:
+
+  * estimator call with one time value per utterance, t of shape (B,)  (reference flow_matching.py:84-97)
+  * compute_loss forward value                                         (reference flow_matching.py:65-107)
+  * plan cache: alternating request shapes reuse their plans / graphs  (reference server.py:93-119 request loop)
+  * calls on different streams are ordered by the library             (one workspace per plan)
+  * host-buffer entry: fresh result tensors, speaker vectors on the host path
+  * the per-launch timeline used by bench.py's roofline.kernel
+"""
+import pytest
+import torch
+
+import matcha_tts_24k_b200 as P
+from matcha_tts_24k_b200 import synthetic as syn
+from conftest import cfm_params, rel_l2
+from oracle import cfm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(channels=(128, 128), dropout=0.05, attention_head_dim=64, n_blocks=1, num_mid_blocks=1, num_heads=2)
+
+
+def pair(dec, solver="euler", precision="fp32", in_channels=200, seed=1234):
+    ora = O.CFM(in_channels, 100, cfm_params(solver), dec).eval()
+    syn.fill_named_seed(ora.estimator, seed)
+    m = P.CFM(in_channels, 100, cfm_params(solver), dec, precision=precision).eval()
+    m.estimator.load_state_dict(ora.estimator.state_dict())
+    return ora, m.cuda()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_estimator_with_per_utterance_time(precision, tol):
+    lengths = [70, 41, 64, 9]
+    ora, m = pair(syn.PROD, precision=precision)
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=7)
+    t = torch.tensor([0.05, 0.5, 0.93, 0.31])
+    with torch.inference_mode():
+        ref = ora.estimator(z, mask, mu, t)
+    v = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t.cuda())
+    err = rel_l2(v.cpu(), ref)
+    print(f"per-utterance t [{precision}]: rel_l2={err:.3e} max_abs={float((v.cpu() - ref).abs().max()):.3e}")
+    assert err <= tol
+    # each utterance equals a scalar-t call with its own time (the time embedding is the only thing that differs)
+    for b in (0, 2):
+        vb = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t[b])
+        if precision == "fp32":
+            assert rel_l2(vb[b].cpu(), v[b].cpu()) <= 1e-6
+    # the planned time grid survives an estimator call: a solve afterwards still matches the oracle
+    m.close()
+
+
+def test_compute_loss_forward_value_matches_oracle():
+    lengths = [50, 33]
+    ora, m = pair(SMALL, precision="fp32")
+    mu, mask, x1, _ = syn.make_inputs(lengths, seed=11)
+    g = torch.Generator().manual_seed(5)
+    t = torch.rand(2, generator=g)
+    x0 = mu + torch.randn(mu.shape, generator=g)
+    # oracle value with the same draws (restating compute_loss with t and x0 injected)
+    tt = t.reshape(2, 1, 1)
+    y = (1 - (1 - ora.sigma_min) * tt) * x0 + tt * x1
+    u = x1 - (1 - ora.sigma_min) * x0
+    with torch.inference_mode():
+        pred = ora.estimator(y, mask, mu, t)
+    ref = torch.nn.functional.mse_loss(pred * mask, u * mask, reduction="sum") / (mask.sum() * u.shape[1])
+    loss = m.compute_loss(x1.cuda(), mask.cuda(), mu.cuda(), t=t.cuda(), x0=x0.cuda())
+    print(f"compute_loss: ours={float(loss):.6f} oracle={float(ref):.6f}")
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    # with its own random draws it runs and is finite (the draws come from torch's CUDA generator, as in the reference)
+    assert torch.isfinite(m.compute_loss(x1.cuda(), mask.cuda(), mu.cuda()))
+    m.close()
+
+
+def test_plan_cache_alternating_shapes():
+    ora, m = pair(SMALL, precision="fp32")
+    cases = []
+    for i, lengths in enumerate(([40], [57], [40, 33])):
+        mu, mask, z, _ = syn.make_inputs(lengths, seed=20 + i)
+        ts = torch.linspace(0, 1, 4)
+        cases.append((lengths, mu.cuda(), mask.cuda(), z.cuda(), ts, ora.solve(z, ts, mu, mask)))
+    first = {}
+    for rnd in range(4):  # A B C A B C ...: from the second round on every plan is cached and its graph replays
+        for i, (lengths, mu, mask, z, ts, ref) in enumerate(cases):
+            out = m.solve(z, ts, mu, mask)
+            assert rel_l2(out.cpu(), ref) <= 2e-5
+            if rnd == 1:
+                first[i] = out.clone()
+            if rnd > 1:
+                assert torch.equal(out, first[i])  # graph replay of the cached plan: bitwise repeatable
+    m.set_option("plan_cache", 1)  # a one-entry cache evicts on every change of shape and still decodes correctly
+    for lengths, mu, mask, z, ts, ref in cases + cases:
+        assert rel_l2(m.solve(z, ts, mu, mask).cpu(), ref) <= 2e-5
+    m.close()
+
+
+def test_calls_on_different_streams_are_ordered():
+    ora, m = pair(SMALL, precision="fp32")
+    lengths = [64, 50]
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=31)
+    mu2, _, z2, _ = syn.make_inputs(lengths, seed=32)
+    ts = torch.linspace(0, 1, 3)
+    ref1, ref2 = ora.solve(z, ts, mu, mask), ora.solve(z2, ts, mu2, mask)
+    mu_d, z_d, mask_d = mu.cuda(), z.cuda(), mask.cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            out1 = m.solve(z_d, ts, mu_d, mask_d)          # asynchronous, on a side stream
+        out2 = m.solve_host(z2, ts, mu2, lengths)            # immediately after, on the library's own stream
+        side.synchronize()
+        assert rel_l2(out1.cpu(), ref1) <= 2e-5 and rel_l2(out2, ref2) <= 2e-5
+    m.close()
+
+
+def test_solve_host_returns_fresh_tensors_and_takes_speakers():
+    S = 16
+    ora, m = pair(SMALL, precision="fp32", in_channels=200 + S)
+    lengths = [30, 22]
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=41)
+    spks = torch.randn(2, S, generator=torch.Generator().manual_seed(1))
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask, spks)
+    a = m.solve_host(z, ts, mu, lengths, spks=spks)
+    b = m.solve_host(z, ts, mu, lengths, spks=spks)
+    assert a.data_ptr() != b.data_ptr() and torch.equal(a, b)
+    assert rel_l2(a, ref) <= 2e-5
+    buf = torch.empty_like(mu).pin_memory()
+    assert m.solve_host(z, ts, mu, lengths, spks=spks, out=buf) is buf and torch.equal(buf, a)
+    with pytest.raises(ValueError, match="speaker"):
+        m.solve_host(z, ts, mu, lengths)  # an estimator with speaker channels never reuses a stale device pointer
+    with pytest.raises(ValueError):
+        m.solve_host(z, ts, mu[:, :80], lengths, spks=spks)
+    m.close()
+
+
+def test_timeline_lists_every_launch():
+    _, m = pair(SMALL, precision="bf16")
+    lengths = [200, 150]
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=51, device="cuda")
+    ts = torch.linspace(0, 1, 3)
+    m.solve(z, ts, mu, mask)
+    rows = m.timeline(z, ts, mu, lengths)
+    tags = {r[0] for r in rows}
+    assert {"qkv", "attention", "out_proj", "ff1_snake", "ff2_copy", "res_conv", "final_proj_ode", "conv_s2", "conv_transpose"} <= tags
+    assert all(r[5] >= 0 for r in rows) and sum(r[4] for r in rows) > 0
+    m.close()

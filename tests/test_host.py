@@ -59,8 +59,28 @@ def test_cfm_surface_matches_reference():
     assert {k: v.data_ptr() for k, v in m._weights.state_dict().items()} == before
     with pytest.raises(ValueError):
         P.CFM(200, 100, cfm_params(), dict(P.synthetic.PROD, down_block_type="conformer"))
-    with pytest.raises(NotImplementedError):
-        m.compute_loss(None, None, None)
+
+
+def test_argument_checks_precede_the_library_call():
+    """The library packs with its own B / F / T; mismatching tensors must raise on the host (reference: conv shape error)."""
+    m = P.CFM(200, 100, cfm_params(), P.synthetic.PROD).eval()
+    mu80, mu100 = torch.zeros(2, 80, 10), torch.zeros(2, 100, 10)
+    with pytest.raises(ValueError, match="80 mel channels"):
+        m._check_shapes(mu80, mu80)
+    with pytest.raises(ValueError, match="disagree"):
+        m._check_shapes(mu100, torch.zeros(2, 100, 12))
+    assert m._check_shapes(mu100, mu100) == (2, 100, 10)
+    with pytest.raises(ValueError, match="1 entries"):
+        m._check_lengths([5], 2, 10)
+    with pytest.raises(ValueError):
+        m._check_lengths([5, 11], 2, 10)
+    with pytest.raises(ValueError, match="speaker channels"):
+        m._check_spks(torch.zeros(2, 96), 2, prep=False)
+    ms = P.CFM(296, 100, cfm_params(), P.synthetic.PROD).eval()
+    with pytest.raises(ValueError, match="missing"):
+        ms._check_spks(None, 2, prep=False)
+    with pytest.raises(ValueError, match="shape"):
+        ms._check_spks(torch.zeros(2, 95), 2, prep=False)
 
 
 def test_cpu_tensors_are_refused():
@@ -95,6 +115,12 @@ def test_lengths_from_mask():
         P.lengths_from_mask(bad)
     with pytest.raises(ValueError):
         P.lengths_from_mask(mask.bool())
+    with pytest.raises(ValueError):
+        P.lengths_from_mask(mask * 0.5)
+    # a half-precision mask of cfg4's length: summing it in its own dtype would round (bf16 has 8 bits of mantissa)
+    long = P.synthetic.sequence_mask(torch.tensor([2812, 300]), 2812).unsqueeze(1)
+    assert P.lengths_from_mask(long.to(torch.bfloat16)) == [2812, 300]
+    assert P.lengths_from_mask(long.to(torch.float16)) == [2812, 300]
 
 
 def test_sharding_is_balanced_and_complete():
