@@ -117,6 +117,10 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *   "snake_warps" 8/12: epilogue warps of the SnakeBeta (FF1) GEMM (default 12)
  *   "graph_after" n: a plan's first n decodes use direct launches, its CUDA graph is captured before decode n + 1
  *                 (0 = capture inside cfm_plan; default 1)
+ *   "ff_fused"    0/1: FeedForward (Linear -> SnakeBeta -> Linear + residual) as ONE kernel with the 4C hidden kept in tensor memory
+ *                 (csrc/ff_fused.cuh) instead of two GEMMs through a [rows, 4C] HBM buffer; plans above "small_tiles" rows only
+ *                 (default 0: measured slower)
+ *   "bn_full" / "bn_half" / "pair_min_k": tile-shape experiments for the N = C GEMMs (0 = automatic)
  *   "plan_cache"  n: plans (row tables + workspace + CUDA graph) kept per handle, least recently used evicted (default 8);
  *                 the only option that does not drop the cached plans */
 int cfm_set_option(cfm_handle* h, const char* key, int32_t value);
@@ -154,6 +158,11 @@ int cfm_debug_gemm(cfm_handle* h, const void* a_bf16, const void* w_bf16, float*
 int cfm_debug_timeline(cfm_handle* h, const float* mu, const float* z, float* out, char* buf, int64_t cap, void* stream);
 /* Debug: every later attn_tc_kernel launch (direct launches only) writes CTA 0's cycle counters to prof_dev[0..16). */
 int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev);
+/* Debug: every later ff_fused_kernel launch (direct launches only) writes CTA 0's cycle counters to prof_dev[0..17): producer
+ * [0] total [1-3] waiting for free Xn / W1 / W2 slots; MMA1 warp [4] total [5] waiting for Xn [6] W1 [14] free H columns; MMA2 warp
+ * [16] total [7] waiting for P (epilogue) [8] W2 [9] Y drained; epilogue warp [10] total [11] waiting for H [12] waiting for Y
+ * [13] residual update; [15] tiles of CTA 0. */
+int cfm_debug_ff_profile(cfm_handle* h, unsigned long long* prof_dev);
 /* Debug: tensor-core GEMM in one epilogue mode (0 bf16 store, 1 fp32 store, 2 fp32 in-place residual add) with per-role
  * cycle counters of CTA 0 written to prof[0..16) (device memory); see csrc/cfm.cu for the slot meanings. */
 int cfm_debug_gemm_profile(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, void* d_bf16, int32_t M,

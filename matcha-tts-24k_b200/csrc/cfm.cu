@@ -19,6 +19,7 @@
 #include "../../include/cfm_b200.h"
 #include "attn.cuh"
 #include "attn_tc.cuh"
+#include "ff_fused.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -51,6 +52,7 @@ struct BlockW {
   NormW ln1, ln3;
   GemmW qkv, out, ff1, ff2;
   float *ea = nullptr, *ib = nullptr;
+  std::vector<float> h_b1, h_ea, h_ib;  // host copies: the fused feed-forward kernel takes them as a by-value kernel parameter
 };
 struct StageW {
   ResnetW res;
@@ -157,12 +159,18 @@ struct cfm_handle {
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
+  int ff_fused = 0;                             // FF1 -> SnakeBeta -> FF2 in one kernel (ff_fused.cuh) for plans above `small_tiles` rows; "ff_fused".
+                                                // Off by default: correct, removes the [rows, 4C] round trip through HBM, but measured
+                                                // 108 / 63 us per full / half resolution block against 96 / 58 us for the two GEMMs
+  int bn_full = 0, bn_half = 0;                 // experiment: tile width for N == C GEMMs with M > / <= 16384 rows (0 = pick_bn); "bn_full", "bn_half"
+  int pair_min_k = 1024;                        // the pair kernel is used when taps * K >= this; "pair_min_k"
   int pair_mode = 1;                            // use the CTA-pair (cta_group::2) GEMM kernel
   int tma_epi = 1 << EPI_RESID;                 // bit m: TMA-store epilogue for EpiMode m.  Measured on cfg2: the in-place
                                                 // residual add through cp.reduce.async.bulk saves 1.2 ms per decode; STORE / SNAKE /
                                                 // MASK are 0-2 ms slower than the transposing epilogue, so they stay off
   long long launch_counter = 0;
   const float* spks = nullptr;  // device (B, S) speaker vectors for the next pack (cfm_set_speakers); S = in_channels - 2 F
+  unsigned long long* ff_prof = nullptr;    // debug: device buffer for ff_fused_kernel's CTA-0 cycle counters
   unsigned long long* attn_prof = nullptr;  // debug: device buffer for attn_tc_kernel's CTA-0 cycle counters
   long long stop_after = -1;  // debug: skip every launch after this many (cfm_debug_stop_after)
   bool stopped() const { return stop_after >= 0 && launch_counter >= stop_after; }
@@ -431,6 +439,10 @@ int load_block(cfm_handle* h, DescMap& dm, const std::string& p, BlockW& b) {
   CKR(dev_alloc_t(h, h->wallocs, &b.ib, 4 * C));
   snake_consts_kernel<<<(4 * C + 255) / 256, 256>>>(al, be, 4 * C, b.ea, b.ib);
   CK(cudaGetLastError());
+  b.h_b1.resize(4 * C), b.h_ea.resize(4 * C), b.h_ib.resize(4 * C);
+  CK(cudaMemcpy(b.h_b1.data(), b.ff1.bias, sizeof(float) * 4 * C, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.h_ea.data(), b.ea, sizeof(float) * 4 * C, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.h_ib.data(), b.ib, sizeof(float) * 4 * C, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -608,6 +620,10 @@ int set_gemm_attrs(cfm_handle* h) {
     const KernelInfo k = tc2_info(bn);
     CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
   }
+  {
+    const KernelInfo k = kinfo_ff_fused();
+    CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+  }
   const KernelInfo k = tc_info(192, 8);  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
   for (int CL = 1; CL <= 4; CL *= 2) {
     cudaLaunchConfig_t cfg;
@@ -640,7 +656,11 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     return 0;
   }
   if (p.K % 64 != 0) return fail(h, CFM_ERR_INVALID, "tensor-core GEMM needs K %% 64 == 0 (K=%d)", p.K);
-  const int bn = (h->small_tiles && p.M <= h->small_tiles) ? pick_bn_small(p.N) : pick_bn(p.N);
+  int bn = (h->small_tiles && p.M <= h->small_tiles) ? pick_bn_small(p.N) : pick_bn(p.N);
+  if (p.N == h->C() && p.M > 1024) {
+    const int o = p.M > 16384 ? h->bn_full : h->bn_half;
+    if (o == 64 || o == 128 || o == 192) bn = o;
+  }
   CUtensorMap tmA[2], tmW;
   for (int i = 0; i < 2; ++i) {
     const int src = p.A[i] ? i : 0;
@@ -659,7 +679,7 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
     else CKR(make_out_tmap(h, &tmO, p.out_act, false, p.N, p.M, p.ld_act));
   }
   // CTA-pair kernel where it measures faster: long reductions (k=3 convs, FF2); short-K GEMMs are epilogue-bound there.
-  const bool pair_ok = h->pair_mode == 2 || (h->pair_mode == 1 && (p.n_taps * p.K >= 1024 || (h->pair_n256 && bn == 256)));
+  const bool pair_ok = h->pair_mode == 2 || (h->pair_mode == 1 && (p.n_taps * p.K >= h->pair_min_k || (h->pair_n256 && bn == 256)));
   p.pair = pair_ok && bn >= 128 ? 1 : 0;
   p.cluster = p.pair ? 1 : h->cluster;
   CKR(make_tmap(h, &tmW, p.W, p.ldw, p.w_rows, p.ldw * 2, 64, p.pair ? bn / 2 : bn / p.cluster));
@@ -869,6 +889,59 @@ int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const vo
   return 0;
 }
 
+// FeedForward (Linear -> SnakeBeta -> Linear, + residual) as one kernel: ff_fused.cuh.
+int run_ff_fused(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const int C = h->C();
+  CKR(tl_mark(h, s, copy_dst ? "ff_fused_copy" : "ff_fused", R.M, C, 4 * C, 2.0 * 2.0 * R.M * C * 4.0 * C));
+  CUtensorMap tmA, tmW1, tmW2, tmX;
+  CKR(make_tmap(h, &tmA, R.Xn, C, R.M, (long long)C * 2, 64, 128));
+  CKR(make_out_tmap(h, &tmX, R.X, true, C, R.M, C));
+  CKR(make_tmap(h, &tmW1, w.ff1.w, w.ff1.Kp, w.ff1.n_stride, (long long)w.ff1.Kp * 2, 64, FfCfg::HC / 2));
+  CKR(make_tmap(h, &tmW2, w.ff2.w, w.ff2.Kp, w.ff2.n_stride, (long long)w.ff2.Kp * 2, 64, C / 4));
+  FfParams p;
+  memset(&p, 0, sizeof p);
+  p.M = R.M, p.C = C;
+  p.b1 = w.ff1.bias, p.ea = w.ea, p.ib = w.ib, p.b2 = w.ff2.bias;
+  p.X = R.X, p.ldx = C;
+  p.copy = static_cast<bf16*>(copy_dst), p.ld_copy = copy_ld, p.row_info = R.info;
+  p.prof = h->ff_prof;
+  const KernelInfo k = kinfo_ff_fused();
+  const int n_tiles = (R.M + 255) / 256;
+  const int pairs = std::min(n_tiles, h->max_clusters[2]);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(pairs * 2), cfg.blockDim = dim3(k.threads), cfg.dynamicSmemBytes = FfCfg::smem_bytes(C), cfg.stream = s;
+  cudaLaunchAttribute attr[3];
+  int n = 0;
+  if (h->win_bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = h->win_ptr;
+    attr[n].val.accessPolicyWindow.num_bytes = h->win_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = 2, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+  ++n;
+  if (h->pdl_now) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  static thread_local FfConsts cst;  // 18 KB by-value kernel parameter (copied by the launch / into the graph node)
+  memcpy(cst.b1, w.h_b1.data(), sizeof(float) * 4 * C);
+  memcpy(cst.ea, w.h_ea.data(), sizeof(float) * 4 * C);
+  memcpy(cst.ib, w.h_ib.data(), sizeof(float) * 4 * C);
+  void* args[] = {&tmA, &tmW1, &tmW2, &tmX, &p, &cst};
+  CK(cudaLaunchKernelExC(&cfg, k.fn, args));
+  return 0;
+}
+
 // BasicTransformerBlock (reference transformer.py:230-303).  If copy_dst != nullptr the FF2 epilogue also writes the
 // masked activation-type copy of the block output there (skip connection / next conv input).
 int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s, bool ln1_done) {
@@ -888,6 +961,8 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
     CKR(launch_gemm(h, p, true, s));
   }
   CKR(run_layernorm(h, R, w.ln3, s));
+  const bool tc = h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  if (tc && h->ff_fused && C % 64 == 0 && C <= FfCfg::MAX_C && R.M > h->small_tiles) return run_ff_fused(h, R, w, copy_dst, copy_ld, s);
   {
     GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.ff1, nullptr, nullptr);
     p.mode = EPI_SNAKE, p.ea = w.ea, p.ib = w.ib, p.out_act = R.ffh, p.ld_act = 4 * C;
@@ -1740,6 +1815,10 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "snake_warps") == 0 && (value == 8 || value == 12)) h->snake_warps = value;
   else if (strcmp(key, "l2_persist_mb") == 0 && value >= 0) return apply_l2_persist(h, value);
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
+  else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
+  else if (strcmp(key, "bn_full") == 0) h->bn_full = value;
+  else if (strcmp(key, "bn_half") == 0) h->bn_half = value;
+  else if (strcmp(key, "pair_min_k") == 0 && value >= 0) h->pair_min_k = value;
   else if (strcmp(key, "direct_epi") == 0 && value >= 0) h->direct_epi = value;
   else if (strcmp(key, "pdl") == 0) h->pdl = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "cluster") == 0 && (value == 1 || value == 2 || value == 4)) h->cluster = value;
@@ -1750,6 +1829,12 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
 int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev) {
   if (!h) return CFM_ERR_INVALID;
   h->attn_prof = prof_dev;
+  return 0;
+}
+
+int cfm_debug_ff_profile(cfm_handle* h, unsigned long long* prof_dev) {
+  if (!h) return CFM_ERR_INVALID;
+  h->ff_prof = prof_dev;
   return 0;
 }
 

@@ -1285,7 +1285,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               __syncwarp();
               if (lane == 0) {
                 if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-                else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+                else ptx::mbar_arrive_remote_relaxed(&tempty_bar[acc], 0);
               }
             });
             continue;
@@ -1298,7 +1298,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               __syncwarp();
               if (lane == 0) {
                 if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-                else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+                else ptx::mbar_arrive_remote_relaxed(&tempty_bar[acc], 0);
               }
             });
             continue;
@@ -1309,7 +1309,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         if (lane == 0) {  // the accumulator of BOTH CTAs must be drained before the leader's MMA thread reuses it
           if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-          else ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+          else ptx::mbar_arrive_remote_relaxed(&tempty_bar[acc], 0);
         }
       }
       if (p.tma_epi) ptx::bulk_wait_all_elect();

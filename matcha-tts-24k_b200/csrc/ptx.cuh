@@ -41,7 +41,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Suspend-time hint of try_wait: the waiting thread is parked by the hardware until the phase completes (or this many ns pass)
 // instead of re-polling - a dozen waiting warps per CTA otherwise burn issue slots and power the capped chip does not have.
-constexpr uint32_t kSuspendHintNs = 0x989680;
+#ifndef CFM_SUSPEND_HINT_NS
+#define CFM_SUSPEND_HINT_NS 0x989680
+#endif
+constexpr uint32_t kSuspendHintNs = CFM_SUSPEND_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -272,6 +275,64 @@ __device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t d
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from TENSOR MEMORY (bf16 pairs, one row per lane, K / 2 32-bit columns) instead of shared memory.
+__device__ __forceinline__ void umma_bf16_pair_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One 64-element K block (four K = 16 steps) of a CTA-pair MMA in ONE asm statement: the descriptors advance by 32 bytes (2 in
+// their >> 4 address field) per step.  Cuts the per-MMA issue overhead (predicate set-up, elect, operand moves into uniform
+// registers) to a quarter - needed when the MMA itself is short (N = 64: 32 cycles).
+__device__ __forceinline__ void umma_bf16_pair_k64_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                         uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, t, e;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\tadd.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\tadd.u64 b3, %2, 6;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+// Same for an A operand in tensor memory and TWO accumulators (the two column halves of a wide output): per K = 16 step the A
+// columns are a0..a3 (8 packed 32-bit columns each), B advances by 32 bytes; 8 MMAs in one statement.
+__device__ __forceinline__ void umma_bf16_pair_ts_k64x2_elect(uint32_t tmem_d0, uint32_t tmem_d1, uint32_t a0, uint32_t a1, uint32_t a2,
+                                                              uint32_t a3, uint64_t desc_b0, uint64_t desc_b1, uint32_t idesc,
+                                                              uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, t, e;\n\t.reg .b64 x1, y1, x2, y2, x3, y3;\n\t"
+      "setp.ne.b32 p, %9, 0;\n\t"
+      "setp.eq.b32 t, %9, %9;\n\t"
+      "add.u64 x1, %6, 2;\n\tadd.u64 y1, %7, 2;\n\t"
+      "add.u64 x2, %6, 4;\n\tadd.u64 y2, %7, 4;\n\t"
+      "add.u64 x3, %6, 6;\n\tadd.u64 y3, %7, 6;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%2], %6, %8, p;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], [%2], %7, %8, p;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%3], x1, %8, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], [%3], y1, %8, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%4], x2, %8, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], [%4], y2, %8, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%5], x3, %8, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], [%5], y3, %8, t;\n\t}\n"
+      :
+      : "r"(tmem_d0), "r"(tmem_d1), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "l"(desc_b0), "l"(desc_b1), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -364,6 +425,20 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      :
+      : "r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+
+// Same with relaxed semantics.  The release form above blocks the issuing thread until its CTA's earlier memory traffic is visible
+// cluster-wide: measured 0.4-1.2 us per call inside a busy CTA pair (ff_fused.cuh profile).  Hand-offs of TENSOR-MEMORY contents do
+// not need it: tcgen05.wait::ld / ::st complete the accesses and tcgen05.fence::before_thread_sync orders them before the arrive;
+// the waiter issues tcgen05.fence::after_thread_sync.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
       :
       : "r"(smem_u32(bar)), "r"(rank)
       : "memory");

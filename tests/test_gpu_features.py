@@ -144,3 +144,25 @@ def test_timeline_lists_every_launch():
     assert {"qkv", "attention", "out_proj", "ff1_snake", "ff2_copy", "res_conv", "final_proj_ode", "conv_s2", "conv_transpose"} <= tags
     assert all(r[5] >= 0 for r in rows) and sum(r[4] for r in rows) > 0
     m.close()
+
+
+@pytest.mark.parametrize("dec,lengths", [(syn.PROD, [300, 171, 64]), (syn.DEFAULT, [257, 130]), (SMALL, [150, 97])])
+def test_fused_feed_forward_kernel_matches_two_gemm_schedule(dec, lengths):
+    """ff_fused.cuh (FF1 -> SnakeBeta -> FF2 in one kernel, hidden activation in tensor memory, A operand of the second GEMM read
+    from TMEM) against the default two-GEMM schedule and the oracle: solve x2, bf16 tolerance; "small_tiles" 0 sends every
+    resolution through the fused kernel."""
+    ora, m = pair(dec, precision="bf16")
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=61)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    outs = {}
+    m.refresh(torch.device("cuda", 0))
+    for fused in (0, 1):
+        m.set_option("small_tiles", 0)
+        m.set_option("ff_fused", fused)
+        outs[fused] = m.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+        err = rel_l2(outs[fused], ref)
+        print(f"ff_fused={fused}: rel_l2 vs oracle {err:.3e}")
+        assert err <= 1e-2
+    assert rel_l2(outs[1], outs[0]) <= 1e-2
+    m.close()
