@@ -233,6 +233,44 @@ def gpu_pytorch_baseline(dev, names=("cfg2", "cfg1"), n_timed=5, with_compile=Tr
     return out
 
 
+def cfg3_strong_scaling(n_gpus: int, precision: str):
+    """BASELINE config 3 as the product runs it: ONE process drives every GPU of the box (ShardedCFM: one library handle and host
+    thread per GPU, utterances dealt by cost, per-utterance H2D / D2H at the original indices, no collective).  Measured by rank 0
+    while the other ranks of the torchrun job wait on a CPU barrier.  t1 = the same 256-utterance batch on one GPU through the same
+    host-buffer entry.  Wall clock around the call (it returns when the result is on the host)."""
+    import matcha_tts_24k_b200 as P
+    lengths = P.synthetic.config_lengths("cfg3")
+    cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
+    mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=5)
+    mu, z = mu.pin_memory(), z.pin_memory()
+    out = torch.empty_like(mu).pin_memory()
+    ts = torch.linspace(0, 1, N_STEPS_ODE + 1)
+
+    def run(devices, reps):
+        sh = P.ShardedCFM(200, 100, cp, P.synthetic.PROD, devices=devices, precision=precision)
+        for r in sh.replicas:
+            P.synthetic.fill_named_seed(r.estimator, 1234)
+        for _ in range(3):  # plan, direct-launch decode, graph capture
+            sh.solve_host(z, ts, mu, lengths, out=out)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            sh.solve_host(z, ts, mu, lengths, out=out)
+            times.append((time.perf_counter() - t0) * 1e3)
+        shards = sh.last_shards
+        sh.close()
+        return statistics.median(times), shards
+
+    t1, _ = run([0], 3)
+    tn, shards = run(list(range(n_gpus)), 7)
+    cost = [sum(P.sharding.utterance_cost(lengths[i], 384) for i in s) for s in shards]
+    return {"workload": "cfg3: B=256 mixed 2-12 s, mask-packed, 10 Euler steps, host buffers (H2D + decode + D2H per GPU)",
+            "api": "ShardedCFM.solve_host -> cfm_solve_host_indexed / cfm_synchronize, one process, one host thread per GPU",
+            "n_gpus": n_gpus, "t1_ms": t1, "tn_ms": tn, "speedup": t1 / tn, "value": sum(lengths) / (tn * 1e-3), "unit": UNIT,
+            "imbalance": max(cost) / (sum(cost) / len(cost)), "utterances_per_gpu": [len(s) for s in shards],
+            "frames_per_gpu": [sum(lengths[i] for i in s) for s in shards]}
+
+
 def kernel_table(rows, peak_tflops):
     """Aggregates cfm_debug_timeline rows by launch class: in-situ time, share of the step, achieved TFLOP/s."""
     agg = {}
@@ -262,6 +300,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-on-the-same-GPU baseline leg")
     ap.add_argument("--no-compile-baseline", action="store_true", help="skip the torch.compile part of that leg")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the extra cfg3 strong-scaling record (ShardedCFM driven by rank 0)")
     ap.add_argument("--ode-steps", type=int, default=N_STEPS_ODE, help="Euler steps per decode (BASELINE config 5 sweeps 2/4/10/32)")
     ap.add_argument("--solver", default="euler", choices=["euler", "midpoint", "heun3", "rk4"],
                     help="fixed-grid solver (the reference ships midpoint with 4 steps: matcha/inference.py:39-40)")
@@ -435,6 +474,18 @@ def main():
         torch.set_num_threads(threads)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{len(sample)} utterances of {desc}, full 10-step Euler decode, median of 2 (~{2 * sec:.0f} s)"}
+    if dist and args.workload == "cfg2" and not args.no_strong:
+        # one process (rank 0) drives all GPUs through the product's multi-GPU API; the others wait on the CPU
+        model.close()
+        torch.cuda.synchronize(dev)
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                line["extra"] = {"cfg3_strong": cfg3_strong_scaling(world, args.precision)}
+            except Exception as e:  # noqa: BLE001
+                line["extra"] = {"cfg3_strong": {"error": f"{type(e).__name__}: {e}"[:300]}}
+        dist.barrier(group=cpu_group)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:

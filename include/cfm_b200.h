@@ -132,6 +132,17 @@ int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out);
 /* cfm_solve_host for an estimator with S = in_channels - 2 * out_channels > 0 speaker channels: spks = host fp32 (batch, S). */
 int cfm_solve_host_spks(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out);
 
+/* Multi-GPU (utterance-sharded, no collective: SURVEY.md 8(e); BASELINE config 3).  One handle per GPU, each planned with the
+ * lengths of ITS utterances; this call makes the handle decode utterances index[0 .. planned batch) of a host batch of n_total
+ * utterances: per-utterance H2D from mu / z (n_total, out_channels, t_pad) [spks (n_total, S) or NULL], the decode, per-utterance
+ * D2H into the same positions of out.  Returns after ENQUEUEING (the handle's own stream): the host starts every GPU, then calls
+ * cfm_synchronize on each.  Host buffers should be pinned (pageable memory makes the copies synchronous).  The host-side dealing of
+ * utterances to GPUs (longest processing time first over the cost L (274 C^2 + 1800 C) + 24 C L^2) is sharding.py. */
+int cfm_solve_host_indexed(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out, const int32_t* index,
+                           int32_t n_total);
+/* Blocks until everything the handle has enqueued, on any stream, is complete. */
+int cfm_synchronize(cfm_handle* h);
+
 /* Replaces: one call of Decoder.forward(x, mask, mu, t) (decoder.py:359-426) for the planned shapes:
  * v = estimator(x, mask, mu, t); padded frames of v are zero.  Asynchronous on `stream`. */
 int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream);

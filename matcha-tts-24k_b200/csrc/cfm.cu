@@ -1646,6 +1646,51 @@ static int solve_host_impl(cfm_handle* h, const float* mu, const float* z, const
 
 int cfm_solve_host(cfm_handle* h, const float* mu, const float* z, float* out) { return solve_host_impl(h, mu, z, nullptr, out); }
 
+// Sharded host entry: this handle decodes the utterances index[0 .. B) of a HOST batch whose tensors are
+// (n_total, F, t_pad): per-utterance H2D from their positions in the caller's buffers, the decode, per-utterance D2H of the
+// results to the same positions of `out`.  Everything is enqueued on the handle's own stream and the call returns without
+// waiting (cfm_synchronize), so a host thread can start every GPU of the box before it waits for any of them.
+int cfm_solve_host_indexed(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out, const int32_t* index,
+                           int32_t n_total) {
+  if (!h || !mu || !z || !out || !index) return fail(h, CFM_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(h, CFM_ERR_STATE, "cfm_solve_host_indexed before cfm_plan");
+  Plan* pl = h->plan;
+  CK(cudaSetDevice(h->cfg.device));
+  const int S = h->cfg.in_channels - 2 * h->cfg.out_channels;
+  if ((S > 0) != (spks != nullptr)) return fail(h, CFM_ERR_INVALID, "this estimator has %d speaker channels: spks must%s be given", S, S > 0 ? "" : " not");
+  for (int b = 0; b < pl->B; ++b)
+    if (index[b] < 0 || index[b] >= n_total) return fail(h, CFM_ERR_INVALID, "index[%d]=%d outside [0, %d)", b, index[b], n_total);
+  const size_t per = (size_t)h->cfg.out_channels * pl->T, n = (size_t)pl->B * per;
+  cudaStream_t s = h->own_stream;
+  CKR(enter_stream(h, s));
+  if (!pl->stage_mu) {
+    CKR(plan_alloc_t(h, pl, &pl->stage_mu, n));
+    CKR(plan_alloc_t(h, pl, &pl->stage_z, n));
+    CKR(plan_alloc_t(h, pl, &pl->stage_out, n));
+    if (S > 0) CKR(plan_alloc_t(h, pl, &pl->stage_spk, (size_t)pl->B * S));
+  }
+  for (int b = 0; b < pl->B; ++b) {
+    CK(cudaMemcpyAsync(pl->stage_mu + b * per, mu + (size_t)index[b] * per, per * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pl->stage_z + b * per, z + (size_t)index[b] * per, per * 4, cudaMemcpyHostToDevice, s));
+    if (S > 0) CK(cudaMemcpyAsync(pl->stage_spk + (size_t)b * S, spks + (size_t)index[b] * S, (size_t)S * 4, cudaMemcpyHostToDevice, s));
+  }
+  h->spks = S > 0 ? pl->stage_spk : nullptr;
+  CKR(cfm_solve(h, pl->stage_mu, pl->stage_z, pl->stage_out, s));
+  h->spks = nullptr;
+  for (int b = 0; b < pl->B; ++b)
+    CK(cudaMemcpyAsync(out + (size_t)index[b] * per, pl->stage_out + b * per, per * 4, cudaMemcpyDeviceToHost, s));
+  CKR(leave_stream(h, s));
+  return 0;
+}
+
+// Waits for everything this handle has enqueued (on any stream).
+int cfm_synchronize(cfm_handle* h) {
+  if (!h) return CFM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->busy_valid) CK(cudaEventSynchronize(h->busy_event));
+  return 0;
+}
+
 int cfm_solve_host_spks(cfm_handle* h, const float* mu, const float* z, const float* spks, float* out) {
   if (!spks) return fail(h, CFM_ERR_INVALID, "null argument");
   return solve_host_impl(h, mu, z, spks, out);

@@ -166,3 +166,36 @@ def test_fused_feed_forward_kernel_matches_two_gemm_schedule(dec, lengths):
         assert err <= 1e-2
     assert rel_l2(outs[1], outs[0]) <= 1e-2
     m.close()
+
+
+def _sharded_case(devices):
+    lengths = [120, 64, 97, 33, 150, 88, 140]
+    ora, single = pair(SMALL, precision="fp32")
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=71)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    one = single.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+    sh = P.ShardedCFM(200, 100, cfm_params("euler"), SMALL, devices=devices, precision="fp32")
+    sh.load_estimator_state_dict(ora.estimator.state_dict())
+    out = torch.full_like(mu, float("nan")).pin_memory()
+    res = sh.solve_host(z.pin_memory(), ts, mu.pin_memory(), lengths, out=out)
+    assert res is out and torch.isfinite(out).all()
+    assert sorted(i for s in sh.last_shards for i in s) == list(range(len(lengths))) and all(sh.last_shards)
+    assert rel_l2(out, ref) <= 2e-5
+    # utterances do not interact given T: the sharded decode equals the one-GPU decode of the whole batch (fp32 mode: the
+    # stand-alone statistics pass sums in fp64, order-independent to ~1e-16)
+    assert rel_l2(out, one) <= 1e-6
+    again = sh.solve_host(z, ts, mu, lengths)  # pageable inputs, fresh result tensor, cached plans / graphs
+    assert torch.equal(again, out)
+    sh.close()
+    single.close()
+
+
+def test_sharded_decode_two_replicas_on_one_gpu():
+    """The in-process multi-GPU path (ShardedCFM -> cfm_solve_host_indexed / cfm_synchronize) with two handles on device 0."""
+    _sharded_case([0, 0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_decode_two_gpus():
+    _sharded_case([0, 1])
