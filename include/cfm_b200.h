@@ -143,6 +143,21 @@ int cfm_solve_host_indexed(cfm_handle* h, const float* mu, const float* z, const
 /* Blocks until everything the handle has enqueued, on any stream, is complete. */
 int cfm_synchronize(cfm_handle* h);
 
+/* Front of the decode - replaces matcha/inference.py:146-167 (sequence_mask + generate_path, utils/model.py:7-40; the fp32
+ * mu_x @ path matmul, :155-162; downsample = avg_pool1d(k 3, s 2, p 1), utils/model.py:57-68) without materialising the path:
+ *   cfm_front_durations: durations (batch, t_x) device fp32, already rounded / clamped / masked as at inference.py:143 ->
+ *                        cum (batch, t_x) int32 inclusive prefix sums, fine_lengths (batch) = max(sum, 1)      [y_fine_lengths]
+ *   (the host reads fine_lengths: it needs max() for the output shape exactly like fix_len_compatibility's .item(), :148;
+ *    t_pad = 2 ceil(max / 2) and lengths[b] = max((fine + 1) / 2, 1) then go straight to cfm_plan - no mask round trip)
+ *   cfm_front_expand:    mu_x (batch, out_channels, t_x) -> mu_y (batch, out_channels, t_pad), y_mask (batch, t_pad) or NULL
+ * Back - replaces decoder_outputs[:, :, :t_out] and denormalize (inference.py:170-172, utils/model.py:52-54):
+ *   cfm_denormalize:     x (batch, out_channels, t_pad) -> out (batch, out_channels, t_out) = x * std + mean
+ * All asynchronous on `stream`. */
+int cfm_front_durations(cfm_handle* h, const float* durations, int32_t batch, int32_t t_x, int32_t* cum, int32_t* fine_lengths, void* stream);
+int cfm_front_expand(cfm_handle* h, const float* mu_x, const int32_t* cum, const int32_t* fine_lengths, int32_t batch, int32_t t_x,
+                     int32_t t_pad, float* mu_y, float* y_mask, void* stream);
+int cfm_denormalize(cfm_handle* h, const float* x, int32_t batch, int32_t t_pad, int32_t t_out, float mean, float stdv, float* out, void* stream);
+
 /* Replaces: one call of Decoder.forward(x, mask, mu, t) (decoder.py:359-426) for the planned shapes:
  * v = estimator(x, mask, mu, t); padded frames of v are zero.  Asynchronous on `stream`. */
 int cfm_estimator(cfm_handle* h, const float* x, const float* mu, float t, float* v, void* stream);

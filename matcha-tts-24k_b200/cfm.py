@@ -297,6 +297,56 @@ class CFM(torch.nn.Module):
             self.train(was_training)
         return torch.nn.functional.mse_loss(pred * mask, u * mask, reduction="sum") / (torch.sum(mask) * u.shape[1])
 
+    # ------------------------------------------------------------------ front / back of the decode (reference inference.py:146-172)
+    @torch.inference_mode()
+    def expand_encoder_output(self, mu_x, phoneme_durations):
+        """Front of the decode (reference matcha/inference.py:146-167): ``mu_x`` (B, n_feats, Tx) and the integer-valued
+        ``phoneme_durations`` (B, Tx) (rounded, clamped and masked as at inference.py:143) -> ``(mu_y, y_mask, y_lengths)`` with
+        mu_y (B, n_feats, T), y_mask (B, 1, T) float, y_lengths a python list.  The alignment path is never materialised."""
+        mu_x = self._prep(mu_x)
+        dur = self._prep(phoneme_durations)
+        B, F, Tx = mu_x.shape
+        if F != self._weights.cfg.out_channels or tuple(dur.shape) != (B, Tx):
+            raise ValueError("mu_x must be (B, n_feats, Tx) and phoneme_durations (B, Tx)")
+        if self._handle is None or self._device != mu_x.device:
+            self.refresh(mu_x.device)
+        lib, handle = self._lib, self._handle
+        stream = torch.cuda.current_stream(mu_x.device).cuda_stream
+        cum = torch.empty(B, Tx, dtype=torch.int32, device=mu_x.device)
+        fine = torch.empty(B, dtype=torch.int32, device=mu_x.device)
+        N.check(lib, handle, lib.cfm_front_durations(handle, dur.data_ptr(), B, Tx, cum.data_ptr(), fine.data_ptr(), stream))
+        fine_h = fine.tolist()  # the one host round trip of the front: the output shape depends on max() (reference :148)
+        # reference: y_fine_max_length_ = fix_len_compatibility(max) * 2 = 4 ceil(max / 2); mel length T = that // 2 (always even)
+        t_pad = 2 * ((max(fine_h) + 1) // 2)
+        y_lengths = [max((v + 1) // 2, 1) for v in fine_h]
+        mu_y = torch.empty(B, F, t_pad, dtype=torch.float32, device=mu_x.device)
+        y_mask = torch.empty(B, 1, t_pad, dtype=torch.float32, device=mu_x.device)
+        N.check(lib, handle, lib.cfm_front_expand(handle, mu_x.data_ptr(), cum.data_ptr(), fine.data_ptr(), B, Tx, t_pad, mu_y.data_ptr(),
+                                                  y_mask.data_ptr(), stream))
+        return mu_y, y_mask, y_lengths
+
+    @torch.inference_mode()
+    def denormalize(self, decoder_outputs, mel_mean, mel_std, t_out=None):
+        """Back of the decode (reference inference.py:170-172): ``decoder_outputs[:, :, :t_out] * mel_std + mel_mean``."""
+        x = self._prep(decoder_outputs)
+        B, F, T = x.shape
+        t_out = T if t_out is None else int(t_out)
+        if self._handle is None or self._device != x.device:
+            self.refresh(x.device)
+        out = torch.empty(B, F, t_out, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        N.check(self._lib, self._handle, self._lib.cfm_denormalize(self._handle, x.data_ptr(), B, T, t_out, float(mel_mean), float(mel_std),
+                                                                   out.data_ptr(), stream))
+        return out
+
+    @torch.inference_mode()
+    def synthesise_mel(self, mu_x, phoneme_durations, n_timesteps, mel_mean=0.0, mel_std=1.0, temperature: float = 1.0):
+        """inference.py:146-172 in one call: front -> CFM.forward (lengths handed over directly: no mask -> lengths round trip) ->
+        slice + denormalize.  Returns (mel (B, n_feats, max y_length), y_lengths)."""
+        mu_y, y_mask, y_lengths = self.expand_encoder_output(mu_x, phoneme_durations)
+        dec = self.forward(mu_y, y_mask, n_timesteps, temperature=temperature, lengths=y_lengths)
+        return self.denormalize(dec, mel_mean, mel_std, max(y_lengths)), y_lengths
+
     def timeline(self, x, t_span, mu, lengths):
         """cfm_debug_timeline: in-situ time of every launch of one direct-launch decode -> list of (tag, M, N, K, flops, us)."""
         mu_, x_ = self._prep(mu), self._prep(x)

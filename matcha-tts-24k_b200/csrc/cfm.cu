@@ -1683,6 +1683,34 @@ int cfm_solve_host_indexed(cfm_handle* h, const float* mu, const float* z, const
   return 0;
 }
 
+// ---- front / back of the decode (reference matcha/inference.py:146-172); kernels in kernels.cuh
+int cfm_front_durations(cfm_handle* h, const float* durations, int32_t batch, int32_t t_x, int32_t* cum, int32_t* fine_lengths, void* stream) {
+  if (!h || !durations || !cum || !fine_lengths || batch <= 0 || t_x <= 0) return fail(h, CFM_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  front_cumsum_kernel<<<batch, 32, 0, static_cast<cudaStream_t>(stream)>>>(durations, batch, t_x, cum, fine_lengths);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cfm_front_expand(cfm_handle* h, const float* mu_x, const int32_t* cum, const int32_t* fine_lengths, int32_t batch, int32_t t_x,
+                     int32_t t_pad, float* mu_y, float* y_mask, void* stream) {
+  if (!h || !mu_x || !cum || !fine_lengths || !mu_y || batch <= 0 || t_x <= 0 || t_pad <= 0) return fail(h, CFM_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  dim3 grid((t_pad + 127) / 128, batch);
+  front_expand_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(mu_x, cum, fine_lengths, batch, h->cfg.out_channels, t_x, t_pad, mu_y, y_mask);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cfm_denormalize(cfm_handle* h, const float* x, int32_t batch, int32_t t_pad, int32_t t_out, float mean, float stdv, float* out, void* stream) {
+  if (!h || !x || !out || batch <= 0 || t_pad <= 0 || t_out <= 0 || t_out > t_pad) return fail(h, CFM_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const long long rows = (long long)batch * h->cfg.out_channels, n = rows * t_out;
+  back_denormalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, t_pad, t_out, mean, stdv, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Waits for everything this handle has enqueued (on any stream).
 int cfm_synchronize(cfm_handle* h) {
   if (!h) return CFM_ERR_INVALID;

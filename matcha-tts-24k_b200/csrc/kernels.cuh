@@ -450,6 +450,72 @@ static __global__ void gemv_rows_kernel(const float* __restrict__ x, long long l
   }
 }
 
+// ---------------------------------------------------------------------------------- front / back of the decode
+// Reference matcha/inference.py:146-172.  Front: integer phoneme durations -> alignment path (utils/model.py:24-40), encoder
+// output expanded along the path (mu_x @ path, :155-162), averaged over frames 2t-1, 2t, 2t+1 (downsample, utils/model.py:57-68:
+// avg_pool1d k3 s2 p1, zero padding, always / 3).  The path matrix is never materialised: frame t of the fine grid belongs to the
+// phoneme i with cum[i-1] <= t < cum[i], found by binary search in the cumulative durations.
+// Step 1: inclusive cumulative durations per utterance + fine length (sum, clamped to >= 1).  One warp per utterance.
+static __global__ void front_cumsum_kernel(const float* __restrict__ dur, int B, int Tx, int* __restrict__ cum, int* __restrict__ fine_len) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  if (b >= B) return;
+  int carry = 0;
+  for (int i0 = 0; i0 < Tx; i0 += 32) {
+    const int i = i0 + lane;
+    int v = i < Tx ? (int)(long long)dur[(long long)b * Tx + i] : 0;  // .long() of the reference: truncation of an integral float
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (i < Tx) cum[(long long)b * Tx + i] = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) fine_len[b] = max(carry, 1);
+}
+__device__ __forceinline__ int front_phoneme_of(const int* __restrict__ cum, int Tx, int t) {  // first i with cum[i] > t, or -1
+  int lo = 0, hi = Tx;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cum + mid) > t) hi = mid; else lo = mid + 1;
+  }
+  return lo < Tx ? lo : -1;
+}
+// Step 2: mu_y[b, f, t] = (fine[2t-1] + fine[2t] + fine[2t+1]) / 3, fine[u] = mu_x[b, f, phoneme(u)] for u < fine length, else 0;
+// also writes the float mask (t < ceil(fine_len / 2)) the decoder takes.  One thread per (b, t), loop over the mel bins.
+static __global__ void front_expand_kernel(const float* __restrict__ mu_x, const int* __restrict__ cum, const int* __restrict__ fine_len,
+                                           int B, int F, int Tx, int T, float* __restrict__ mu_y, float* __restrict__ y_mask) {
+  const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int* c = cum + (long long)b * Tx;
+  const int fl = min(fine_len[b], __ldg(c + Tx - 1) > 0 ? __ldg(c + Tx - 1) : 0);  // frames the path covers (0 for an all-zero row)
+  int idx[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int u = 2 * t - 1 + k;
+    idx[k] = (u >= 0 && u < fl) ? front_phoneme_of(c, Tx, u) : -1;
+  }
+  const float* src = mu_x + (long long)b * F * Tx;
+  float* dst = mu_y + (long long)b * F * T + t;
+  for (int f = 0; f < F; ++f) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (idx[k] >= 0) a += __ldg(src + (long long)f * Tx + idx[k]);
+    dst[(long long)f * T] = a / 3.f;
+  }
+  if (y_mask) y_mask[(long long)b * T + t] = t < max((fine_len[b] + 1) / 2, 1) ? 1.f : 0.f;
+}
+// Back: mel = x * std + mean on the first t_out frames of every row (denormalize + the [:, :, :y_max_length] slice, :170-172).
+static __global__ void back_denormalize_kernel(const float* __restrict__ x, long long rows, int T, int t_out, float mean, float stdv,
+                                               float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * t_out) return;
+  const long long r = i / t_out;
+  const int t = (int)(i % t_out);
+  out[i] = fmaf(x[r * T + t], stdv, mean);
+}
+
 // ---------------------------------------------------------------------------------- weight packing
 // dst[(tap * n_stride + n) * ldd + k] = src[n * s_n + k * s_k + tap_k[tap] * s_t], zero for k in [K, ldd).
 template <typename T>

@@ -153,5 +153,45 @@ def main():
         print(name, tuple(out.shape), float(out.abs().mean()), len(keys))
 
 
+def front_back_golden():
+    """Front / back of the decode with the reference's OWN functions (matcha/utils/model.py needs only torch): the statements of
+    matcha/inference.py:146-172 executed on seeded inputs."""
+    sys.path.insert(0, "/root/reference")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_utils_model", "/root/reference/matcha/utils/model.py")
+    M = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(M)
+    g = torch.Generator().manual_seed(11)
+    B, F_, Tx = 3, 100, 23
+    x_lengths = torch.tensor([23, 17, 9])
+    x_mask = M.sequence_mask(x_lengths, Tx).unsqueeze(1).float()
+    mu_x = torch.randn(B, F_, Tx, generator=g) * x_mask
+    phoneme_durations = (torch.rand(B, Tx, generator=g) * 6.0 - 0.3)
+    phoneme_durations = phoneme_durations.round().clamp(min=1) * x_mask.squeeze(1)  # inference.py:143
+    # inference.py:146-167, verbatim
+    y_fine_lengths = torch.clamp_min(phoneme_durations.sum(dim=1).long(), 1)
+    y_fine_max_length = y_fine_lengths.max()
+    y_fine_max_length_ = M.fix_len_compatibility(y_fine_max_length) * 2
+    y_fine_mask = M.sequence_mask(y_fine_lengths, y_fine_max_length_).unsqueeze(1).to(x_mask.dtype)
+    attn_mask_fine = x_mask.unsqueeze(-1) * y_fine_mask.unsqueeze(2)
+    attn_fine = M.generate_path(phoneme_durations, attn_mask_fine.squeeze(1)).unsqueeze(1)
+    mu_y_fine = torch.matmul(mu_x.float(), attn_fine.float().squeeze(1))
+    mu_y = M.downsample(mu_y_fine)
+    y_max_length_ = y_fine_max_length_ // 2
+    y_lengths = torch.clamp_min((y_fine_lengths + 1) // 2, 1)
+    y_max_length = y_lengths.max()
+    y_mask = M.sequence_mask(y_lengths, y_max_length_).unsqueeze(1).to(x_mask.dtype)
+    decoder_outputs = torch.randn(B, F_, y_max_length_, generator=g)
+    mel = M.denormalize(decoder_outputs[:, :, :y_max_length], torch.tensor(-5.52), torch.tensor(2.07))  # inference.py:170-172
+    np.savez_compressed(os.path.join(HERE, "front_back.npz"), mu_x=mu_x.numpy(), phoneme_durations=phoneme_durations.numpy(),
+                        x_mask=x_mask.numpy(), mu_y=mu_y.numpy(), y_mask=y_mask.numpy(), y_lengths=y_lengths.numpy(),
+                        y_max_length=int(y_max_length), decoder_outputs=decoder_outputs.numpy(), mel=mel.numpy(), mel_mean=-5.52, mel_std=2.07)
+    print("front_back", tuple(mu_y.shape), y_lengths.tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "front_back":
+        front_back_golden()
+    else:
+        main()
+        front_back_golden()

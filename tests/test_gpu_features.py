@@ -199,3 +199,53 @@ def test_sharded_decode_two_replicas_on_one_gpu():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_decode_two_gpus():
     _sharded_case([0, 1])
+
+
+def test_front_and_back_of_the_decode_match_reference_and_oracle():
+    """cfm_front_durations / cfm_front_expand / cfm_denormalize against the golden vectors made with the reference's own
+    functions (inference.py:146-172) and, on random ragged inputs incl. an all-masked row and odd / even fine lengths, the oracle."""
+    import numpy as np
+    import os
+    from oracle import front_back as FB
+    _, m = pair(SMALL, precision="fp32")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "front_back.npz"))
+    mu_x, dur = torch.from_numpy(g["mu_x"]), torch.from_numpy(g["phoneme_durations"])
+    mu_y, y_mask, y_lengths = m.expand_encoder_output(mu_x.cuda(), dur.cuda())
+    assert y_lengths == g["y_lengths"].tolist() and tuple(mu_y.shape) == g["mu_y"].shape
+    assert torch.equal(y_mask.cpu(), torch.from_numpy(g["y_mask"]))
+    assert torch.allclose(mu_y.cpu(), torch.from_numpy(g["mu_y"]), atol=1e-6, rtol=0)
+    mel = m.denormalize(torch.from_numpy(g["decoder_outputs"]).cuda(), float(g["mel_mean"]), float(g["mel_std"]), int(g["y_max_length"]))
+    assert torch.allclose(mel.cpu(), torch.from_numpy(g["mel"]), atol=1e-6, rtol=0)
+    gen = torch.Generator().manual_seed(3)
+    for B, Tx in ((5, 61), (2, 300), (1, 7)):
+        x_lengths = torch.randint(1, Tx + 1, (B,), generator=gen)
+        x_lengths[0] = Tx
+        x_mask = FB.sequence_mask(x_lengths, Tx).unsqueeze(1).float()
+        mu_x = torch.randn(B, 100, Tx, generator=gen) * x_mask
+        dur = (torch.rand(B, Tx, generator=gen) * 9).round().clamp(min=1) * x_mask.squeeze(1)
+        ref_mu, ref_mask, ref_len, _ = FB.front(mu_x, dur, x_mask)
+        mu_y, y_mask, y_lengths = m.expand_encoder_output(mu_x.cuda(), dur.cuda())
+        assert y_lengths == ref_len.tolist() and torch.equal(y_mask.cpu(), ref_mask)
+        assert torch.allclose(mu_y.cpu(), ref_mu, atol=1e-6, rtol=0)
+    m.close()
+
+
+def test_synthesise_mel_equals_front_decode_back_of_the_oracle():
+    from oracle import front_back as FB
+    ora, m = pair(SMALL, precision="fp32")
+    gen = torch.Generator().manual_seed(9)
+    B, Tx = 2, 40
+    x_lengths = torch.tensor([40, 28])
+    x_mask = FB.sequence_mask(x_lengths, Tx).unsqueeze(1).float()
+    mu_x = torch.randn(B, 100, Tx, generator=gen) * x_mask
+    dur = (torch.rand(B, Tx, generator=gen) * 5).round().clamp(min=1) * x_mask.squeeze(1)
+    mu_y, y_mask, y_lengths, y_max = FB.front(mu_x, dur, x_mask)
+    # the decode draws its seed-42 noise on the GPU (reference flow_matching.py:43-55): replay those draws for the oracle
+    gdev = torch.Generator(device="cuda")
+    gdev.manual_seed(42)
+    z = mu_y + torch.randn(mu_y.shape, generator=gdev, device="cuda").cpu()
+    ref = FB.back(ora.solve(z, torch.linspace(0, 1, 4), mu_y, y_mask), y_max, -5.5, 2.0)
+    mel, lens = m.synthesise_mel(mu_x.cuda(), dur.cuda(), 3, mel_mean=-5.5, mel_std=2.0)
+    assert lens == y_lengths.tolist() and tuple(mel.shape) == tuple(ref.shape)
+    assert rel_l2(mel.cpu(), ref) <= 2e-5
+    m.close()
