@@ -159,6 +159,9 @@ struct cfm_handle {
   int graph_after = 1;                          // decodes of a plan that use direct launches before its CUDA graph is built
                                                 // (0: capture inside cfm_plan); "graph_after" option
   int small_tiles = 1024;                       // GEMMs with M <= this many rows use 64-column tiles (0: never); "small_tiles" option
+  int bf16_mid = 1;                             // tensor-core mode: the conv output between a conv and its GroupNorm-apply and the
+                                                // res_conv output are stored as bf16 (statistics still come from the fp32
+                                                // accumulators), written by row-per-thread epilogues without smem staging; "bf16_mid"
   int ff_fused = 0;                             // FF1 -> SnakeBeta -> FF2 in one kernel (ff_fused.cuh) for plans above `small_tiles` rows; "ff_fused".
                                                 // Off by default: correct, removes the [rows, 4C] round trip through HBM, but measured
                                                 // 108 / 63 us per full / half resolution block against 96 / 58 us for the two GEMMs
@@ -738,13 +741,19 @@ Res res_of(cfm_handle* h, Plan* pl, int r, const LaneDef& ln) {
   return v;
 }
 
-template <typename T, bool PRECISE>
-int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const double* stats, const float* resid, const NormW& ln, cudaStream_t s) {
+// bf16 conv / res_conv outputs (cfm_handle::bf16_mid): tensor-core schedule with fused statistics only
+bool mid16(const cfm_handle* h) {  // (the row-per-thread statistics assume at most one group boundary per 32 columns: C >= 256)
+  return h->bf && h->bf16_mid && h->cfg.channels % 32 == 0 && h->cfg.channels / 8 >= 32 &&
+         !(h->cfg.flags & (CFM_FLAG_SIMT_GEMM | CFM_FLAG_UNFUSED_STATS));
+}
+
+template <typename T, bool PRECISE, typename HT>
+int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const double* stats, const void* resid, const NormW& ln, cudaStream_t s) {
   const int C = h->C();
   const int blocks = (R.M * 32 + 255) / 256;
 #define CFM_GN_LN(NCH)                                                                                                     \
-  return launch_ex(h, gn_apply_ln_kernel<T, PRECISE, NCH>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, \
-                   R.M, C / 8, (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, resid, (long long)C, R.X,   \
+  return launch_ex(h, gn_apply_ln_kernel<T, PRECISE, NCH, HT>, dim3(blocks), dim3(256), 0, s, 1, (const HT*)R.hraw, (long long)C, \
+                   R.M, C / 8, (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, (const HT*)resid, (long long)C, R.X,   \
                    (long long)C, (const float*)ln.gamma, (const float*)ln.beta, static_cast<T*>(R.Xn), (long long)C)
   switch (C / 128) {
     case 1: CFM_GN_LN(1);
@@ -756,7 +765,7 @@ int launch_gn_ln(cfm_handle* h, const Res& R, const NormW& gn, const double* sta
 }
 
 // `fuse_ln` != nullptr (block2 of a resnet followed by a transformer stack, C % 128 == 0): also emits LayerNorm(out) -> R.Xn.
-int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const float* resid,
+int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int site, const float* addvec, const void* resid,
                  float* out_f32, void* out_act, long long ld_act, cudaStream_t s, const NormW* fuse_ln = nullptr,
                  long long addvec_stride = 0) {
   if (h->stopped()) return 0;
@@ -765,17 +774,22 @@ int run_gn_apply(cfm_handle* h, Plan* pl, const Res& R, const NormW& gn, int sit
   CKR(tl_mark(h, s, fuse_ln ? "gn_apply_ln" : "gn_apply", R.M, C, 0, 0.0));
   const double* stats = pl->stats + (long long)site * pl->B * 16;
   if (fuse_ln) {
-    if (h->bf) return launch_gn_ln<bf16, false>(h, R, gn, stats, resid, *fuse_ln, s);
-    return launch_gn_ln<float, true>(h, R, gn, stats, resid, *fuse_ln, s);
+    if (mid16(h)) return launch_gn_ln<bf16, false, bf16>(h, R, gn, stats, resid, *fuse_ln, s);
+    if (h->bf) return launch_gn_ln<bf16, false, float>(h, R, gn, stats, resid, *fuse_ln, s);
+    return launch_gn_ln<float, true, float>(h, R, gn, stats, resid, *fuse_ln, s);
   }
   const long long items = (long long)R.M * (C / 8);
   const int blocks = (int)((items + 255) / 256);
-  if (h->bf)
-    return launch_ex(h, gn_apply_kernel<bf16, false>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, resid, (long long)C,
+  if (mid16(h))
+    return launch_ex(h, gn_apply_kernel<bf16, false, bf16>, dim3(blocks), dim3(256), 0, s, 1, (const bf16*)R.hraw, (long long)C, R.M, C, C / 8,
+                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, (const bf16*)resid, (long long)C,
                      out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
-  return launch_ex(h, gn_apply_kernel<float, true>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
-                   (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, resid, (long long)C,
+  if (h->bf)
+    return launch_ex(h, gn_apply_kernel<bf16, false, float>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
+                     (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, (const float*)resid, (long long)C,
+                     out_f32, (long long)C, static_cast<bf16*>(out_act), ld_act);
+  return launch_ex(h, gn_apply_kernel<float, true, float>, dim3(blocks), dim3(256), 0, s, 1, (const float*)R.hraw, (long long)C, R.M, C, C / 8,
+                   (const int*)R.info, stats, (const double*)gn.bias_gsum, (const UttTable*)R.utt, (const float*)gn.gamma, (const float*)gn.beta, addvec, addvec_stride, (const float*)resid, (long long)C,
                    out_f32, (long long)C, static_cast<float*>(out_act), ld_act);
 }
 
@@ -787,6 +801,7 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
   p.mode = EPI_STATS;
   h->tag = w.K >= 2 * h->C() ? "conv3_stats_2C" : (w.K == h->C() ? "conv3_stats_C" : "conv3_stats_in");
   p.out_f32 = R.hraw, p.ld_f32 = h->C();
+  if (mid16(h)) p.mode = EPI_STATS16, p.out_act = R.hraw, p.ld_act = h->C();  // bf16 result in the same buffer
   p.row_info = R.info;
   p.stats = pl->stats + (long long)site * pl->B * 16;
   p.group_ch = h->C() / 8;
@@ -797,7 +812,7 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
     h->launch_counter++;
     CKR(tl_mark(h, s, "gn_stats", R.M, h->C(), 0, 0.0));
     const int items = R.M * 8;
-    gn_stats_kernel<<<(items + 255) / 256, 256, 0, s>>>(R.hraw, h->C(), R.M, h->C(), h->C() / 8, R.info, p.stats);
+    gn_stats_kernel<float><<<(items + 255) / 256, 256, 0, s>>>(R.hraw, h->C(), R.M, h->C(), h->C() / 8, R.info, p.stats);
     CK(cudaGetLastError());
   }
   return 0;
@@ -878,6 +893,7 @@ int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const vo
     GemmParams p = gemm_base(R.M, A, lda, R.M, w.res, nullptr, nullptr);
     p.mode = EPI_STATS, p.fused_stats = 0;
     p.out_f32 = R.rres, p.ld_f32 = C;
+    if (mid16(h)) p.mode = EPI_STORE, p.out_act = R.rres, p.ld_act = C;  // bf16 result, direct-store epilogue
     h->tag = "res_conv";
     CKR(launch_gemm(h, p, true, s));
   }
@@ -1811,8 +1827,8 @@ int cfm_debug_read(cfm_handle* h, const char* name, float* host_dst, int64_t max
   struct Ent { const char* n; const void* p; long long r, c; bool act; };
   const Ent table[] = {
       {"xin", pl->xin, pl->M1, pl->xin_ld, true},   {"xstate", pl->xstate, pl->M1, F, false},
-      {"vout", pl->vout, pl->M1, F, false},         {"hraw1", pl->hraw[0], pl->M1, C, false},
-      {"hraw2", pl->hraw[1], pl->M2, C, false},     {"rres1", pl->rres[0], pl->M1, C, false},
+      {"vout", pl->vout, pl->M1, F, false},         {"hraw1", pl->hraw[0], pl->M1, C, mid16(h)},
+      {"hraw2", pl->hraw[1], pl->M2, C, mid16(h)},  {"rres1", pl->rres[0], pl->M1, C, mid16(h)},
       {"X1", pl->X[0], pl->M1, C, false},           {"X2", pl->X[1], pl->M2, C, false},
       {"hact1", pl->hact[0], pl->M1, C, true},      {"hact2", pl->hact[1], pl->M2, C, true},
       {"Xn1", pl->Xn[0], pl->M1, C, true},          {"qkv1", pl->qkv[0], pl->M1, 3 * I, true},
@@ -1889,6 +1905,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "l2_persist_mb") == 0 && value >= 0) return apply_l2_persist(h, value);
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
+  else if (strcmp(key, "bf16_mid") == 0) h->bf16_mid = value != 0;
   else if (strcmp(key, "bn_full") == 0) h->bn_full = value;
   else if (strcmp(key, "bn_half") == 0) h->bn_half = value;
   else if (strcmp(key, "pair_min_k") == 0 && value >= 0) h->pair_min_k = value;

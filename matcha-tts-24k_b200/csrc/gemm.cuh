@@ -29,6 +29,7 @@ enum EpiMode : int {
   EPI_SNAKE = 3,  // h = acc + bias; out_act = h + sin^2(h * ea) * ib     (reference transformer.py:68-75)
   EPI_MASK = 4,   // out_act = valid ? acc + bias : 0
   EPI_ODE = 5,    // v = valid ? acc + bias : 0; y = base + c_v v + sum c_k[i] k_i; fixed-grid ODE stage update
+  EPI_STATS16 = 6,  // out_act = bf16(acc + bias), GroupNorm partial sums from the fp32 values (tensor-core path only)
 };
 
 constexpr int ROW_VALID = 1 << 30;   // row holds a valid mel frame (mask == 1)
@@ -880,6 +881,132 @@ __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32
 }
 
 // ------------------------------------------------------------------------------------------------
+// Conv + GroupNorm statistics with a bf16 result (EPI_STATS16): row-per-thread like epilogue_tile_direct - the accumulator row
+// leaves with 256-bit stores, no shared-memory transpose - and the statistics are taken from the fp32 values on the way: a
+// thread sums its own row over the columns of the current GroupNorm group, the warp combines the 32 rows with shuffles when a
+// group ends (a 32-column unit holds at most one group boundary) and one lane adds the pair to the fp64 sums.  Warps whose 32
+// rows hold two utterances let every lane add for itself (rare: one warp per utterance boundary).
+// The row flags are loaded by the caller BEFORE it waits for the accumulator (their L2 latency otherwise opens every tile's epilogue).
+template <int BN, typename Release>
+__device__ __forceinline__ void epilogue_tile_stats16(const GemmParams& p, uint32_t taddr, int m0, int n0, int half, int lane, int info,
+                                                      Release&& release) {
+  constexpr int UNITS = BN / 32;
+  const int m = m0 + lane;
+  const bool in = p.fused_stats != 0 && (info & ROW_INSTAT) != 0;
+  const int utt = info & ROW_UTT_MASK;
+  const uint32_t in_mask = __ballot_sync(0xffffffffu, in);
+  const int wutt = __shfl_sync(0xffffffffu, utt, in_mask ? __ffs(in_mask) - 1 : 0);
+  const bool uni = __all_sync(0xffffffffu, !in || utt == wutt);
+  const uint32_t b_mask = __ballot_sync(0xffffffffu, in && utt != wutt);  // rows of a second utterance, if any
+  const int utt_b = __shfl_sync(0xffffffffu, utt, b_mask ? __ffs(b_mask) - 1 : 0);
+  const bool two = !uni && __all_sync(0xffffffffu, !in || utt == wutt || utt == utt_b);
+  bf16* orow = reinterpret_cast<bf16*>(p.out_act) + (long long)m * p.ld_act;
+  float cs = 0.f, css = 0.f;
+  int cur_g = -1;
+  auto flush = [&]() {  // the sums of group cur_g are complete for this warp's rows
+    if (in_mask != 0u) {
+      if (uni) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o), css += __shfl_xor_sync(0xffffffffu, css, o);
+        if (lane == 0) {
+          atomicAdd(p.stats + ((long long)wutt * 8 + cur_g) * 2, (double)cs);
+          atomicAdd(p.stats + ((long long)wutt * 8 + cur_g) * 2 + 1, (double)css);
+        }
+      } else if (two) {  // rows of two utterances (sorted): one reduction per utterance, two lanes add
+        float sa = (in && utt == wutt) ? cs : 0.f, qa = (in && utt == wutt) ? css : 0.f;
+        float sb = (in && utt == utt_b) ? cs : 0.f, qb = (in && utt == utt_b) ? css : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o), qa += __shfl_xor_sync(0xffffffffu, qa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o), qb += __shfl_xor_sync(0xffffffffu, qb, o);
+        }
+        if (lane < 2) {
+          const int uu = lane == 0 ? wutt : utt_b;
+          atomicAdd(p.stats + ((long long)uu * 8 + cur_g) * 2, (double)(lane == 0 ? sa : sb));
+          atomicAdd(p.stats + ((long long)uu * 8 + cur_g) * 2 + 1, (double)(lane == 0 ? qa : qb));
+        }
+      } else if (in) {  // three or more utterances inside 32 rows (very short utterances): every lane for itself
+        atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2, (double)cs);
+        atomicAdd(p.stats + ((long long)utt * 8 + cur_g) * 2 + 1, (double)css);
+      }
+    }
+    cs = css = 0.f;
+  };
+  uint32_t ra[16], rb[16];
+  bool released = false;
+  if (half < UNITS) {
+    ptx::tmem_ld16(taddr + half * 32, ra);
+    ptx::tmem_ld16(taddr + half * 32 + 16, rb);
+  }
+#pragma unroll 1
+  for (int u = half; u < UNITS; u += 2) {
+    const int n = n0 + u * 32;
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]), v[16 + i] = __uint_as_float(rb[i]);
+    if (u + 2 < UNITS) {
+      ptx::tmem_ld16(taddr + (u + 2) * 32, ra);
+      ptx::tmem_ld16(taddr + (u + 2) * 32 + 16, rb);
+    } else {
+      release();
+      released = true;
+    }
+    if (n >= p.N) continue;
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+        v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+      }
+    }
+    if (m < p.M) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 hb = __floats2bfloat162_rn(v[16 * hlf + 2 * i], v[16 * hlf + 2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        stg256(orow + n + 16 * hlf, w);
+      }
+    }
+    if (p.fused_stats) {
+      const int g_lo = n / p.group_ch;
+      const int bnd = (g_lo + 1) * p.group_ch - n;  // columns [0, bnd) of the unit belong to group g_lo
+      if (g_lo != cur_g) {
+        if (cur_g >= 0) flush();
+        cur_g = g_lo;
+      }
+      if (bnd >= 32) {  // the whole unit lies in one group (warp-uniform): four independent chains
+        float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f, qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          sa += v[i], sb += v[i + 1], sc += v[i + 2], sd += v[i + 3];
+          qa = fmaf(v[i], v[i], qa), qb = fmaf(v[i + 1], v[i + 1], qb), qc = fmaf(v[i + 2], v[i + 2], qc), qd = fmaf(v[i + 3], v[i + 3], qd);
+        }
+        if (in) cs += (sa + sb) + (sc + sd), css += (qa + qb) + (qc + qd);
+      } else {
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f, s3 = 0.f, q3 = 0.f;  // even / odd columns x (below, above) the boundary
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float x = v[i], y = v[i + 1];
+          if (i < bnd) s0 += x, q0 = fmaf(x, x, q0); else s1 += x, q1 = fmaf(x, x, q1);
+          if (i + 1 < bnd) s2 += y, q2 = fmaf(y, y, q2); else s3 += y, q3 = fmaf(y, y, q3);
+        }
+        if (in) cs += s0 + s2, css += q0 + q2;
+        flush();
+        cur_g = g_lo + 1;
+        if (in) cs = s1 + s3, css = q1 + q3;
+      }
+    }
+  }
+  if (cur_g >= 0) flush();
+  if (!released) release();
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 implementation.
 template <int BN, int NEW = 8>  // NEW = epilogue warps (8, or 12 for the SnakeBeta GEMM whose epilogue is the bottleneck)
 struct TcCfg {
@@ -1063,9 +1190,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         const int m0 = ((tile / n_tiles) * CL + crank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
+        int info_pre = 0;  // row flags requested before the accumulator wait: their latency hides under the MMAs of this tile
+        if constexpr (MODE == EPI_STATS16) info_pre = load_row_info(p, m0 + lane);
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STATS16) {
+          epilogue_tile_stats16<BN>(p, taddr, m0, n0, half, lane, info_pre, [&] {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          });
+          continue;
+        }
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK) {
           if (NEW == 8 && p.direct_epi) {
             epilogue_tile_direct<BN, MODE>(p, taddr, m0, n0, half, lane, [&] {
@@ -1100,6 +1237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       case EPI_RESID: run(std::integral_constant<int, EPI_RESID>{}); break;
       case EPI_SNAKE: run(std::integral_constant<int, EPI_SNAKE>{}); break;
       case EPI_MASK: run(std::integral_constant<int, EPI_MASK>{}); break;
+      case EPI_STATS16: run(std::integral_constant<int, EPI_STATS16>{}); break;
       default: run(std::integral_constant<int, EPI_ODE>{}); break;
     }
   }
@@ -1275,9 +1413,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         const int m0 = ((tile / n_tiles) * 2 + rank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
+        int info_pre = 0;  // row flags requested before the accumulator wait: their latency hides under the MMAs of this tile
+        if constexpr (MODE == EPI_STATS16) info_pre = load_row_info(p, m0 + lane);
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (MODE == EPI_STATS16) {
+          epilogue_tile_stats16<BN>(p, taddr, m0, n0, half, lane, info_pre, [&] {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+              else ptx::mbar_arrive_remote_relaxed(&tempty_bar[acc], 0);
+            }
+          });
+          continue;
+        }
         if constexpr (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK) {
           if (p.direct_epi) {
             epilogue_tile_direct<BN, MODE>(p, taddr, m0, n0, half, lane, [&] {
@@ -1321,6 +1472,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       case EPI_RESID: run(std::integral_constant<int, EPI_RESID>{}); break;
       case EPI_SNAKE: run(std::integral_constant<int, EPI_SNAKE>{}); break;
       case EPI_MASK: run(std::integral_constant<int, EPI_MASK>{}); break;
+      case EPI_STATS16: run(std::integral_constant<int, EPI_STATS16>{}); break;
       default: run(std::integral_constant<int, EPI_ODE>{}); break;
     }
   }

@@ -51,6 +51,21 @@ __device__ __forceinline__ float mish_precise(float x) {
   return x * (n / (n + 2.f));
 }
 
+// 4 / 8 consecutive values of an fp32 or bf16 row (the conv output and the res_conv output are bf16 in the tensor-core mode)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void ld8(const float* p, float4& lo, float4& hi) { lo = ld4(p), hi = ld4(p + 4); }
+__device__ __forceinline__ void ld8(const bf16* p, float4& lo, float4& hi) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z)), d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+  lo = make_float4(a.x, a.y, b.x, b.y), hi = make_float4(c.x, c.y, d.x, d.y);
+}
+
 // ---------------------------------------------------------------------------------- pack / unpack
 // (B, F, T) fp32 channels-first  ->  rows [start_b + t], columns [col0, col0 + F) of a token-major buffer.
 // Rows t >= L of the utterance's segment are written as zero.  Optionally also writes the fp32 state.
@@ -122,17 +137,18 @@ __global__ void pack_speaker_kernel(const float* __restrict__ spks, int S, const
 
 // ---------------------------------------------------------------------------------- GroupNorm
 // Stand-alone statistics pass (fp32 mode and the debug path; the tensor-core GEMM fuses this into its epilogue).
-static __global__ void gn_stats_kernel(const float* __restrict__ h, long long ld, int M, int C, int group_ch,
+template <typename HT>
+__global__ void gn_stats_kernel(const HT* __restrict__ h, long long ld, int M, int C, int group_ch,
                                 const int* __restrict__ row_info, double* __restrict__ stats) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row, group)
   const int m = idx >> 3, g = idx & 7;
   if (m >= M) return;
   const int info = row_info[m];
   if (!(info & ROW_INSTAT)) return;
-  const float* p = h + (long long)m * ld + g * group_ch;
+  const HT* p = h + (long long)m * ld + g * group_ch;
   float s = 0.f, ss = 0.f;
   for (int i = 0; i < group_ch; ++i) {
-    float v = p[i];
+    float v = ActIO<HT>::ld(p + i);
     s += v;
     ss = fmaf(v, v, ss);
   }
@@ -161,12 +177,12 @@ static __global__ void gn_finalize_kernel(const double* __restrict__ stats, cons
 }
 
 // y = valid ? Mish(GN(h)) + addvec[c] : 0;  y += resid[m, c];  -> out_f32 and/or out_act.   8 channels per thread.
-template <typename T, bool PRECISE>
-__global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int M, int C, int group_ch,
+template <typename T, bool PRECISE, typename HT = float>  // HT: storage type of the conv output h and of resid
+__global__ void gn_apply_kernel(const HT* __restrict__ h, long long ld_h, int M, int C, int group_ch,
                                 const int* __restrict__ row_info, const double* __restrict__ stats,
                                 const double* __restrict__ bias_gsum, const UttTable* __restrict__ utt,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ addvec, long long addvec_utt_stride, const float* __restrict__ resid,
+                                const float* __restrict__ addvec, long long addvec_utt_stride, const HT* __restrict__ resid,
                                 long long ld_resid, float* __restrict__ out_f32, long long ld_f32, T* __restrict__ out_act,
                                 long long ld_act) {
   // addvec: time-embedding projection added after Mish (reference decoder.py:60); one vector for the batch (stride 0) or one
@@ -179,13 +195,10 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
   const int c = (int)(idx % c8) * 8;
   // every load that does not depend on the row flags is issued up front: one memory round trip instead of three
   const int info = __ldg(row_info + m);
-  const float4 h0 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c);
-  const float4 h1 = *reinterpret_cast<const float4*>(h + (long long)m * ld_h + c + 4);
+  float4 h0, h1;
+  ld8(h + (long long)m * ld_h + c, h0, h1);
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-  if (resid) {
-    r0 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c);
-    r1 = *reinterpret_cast<const float4*>(resid + (long long)m * ld_resid + c + 4);
-  }
+  if (resid) ld8(resid + (long long)m * ld_resid + c, r0, r1);
   const bool valid = (info & ROW_VALID) != 0;
   float y[8];
 #pragma unroll
@@ -238,12 +251,12 @@ __global__ void gn_apply_kernel(const float* __restrict__ h, long long ld_h, int
 //   x  = (valid ? Mish(GN(h)) : 0) + resid     -> fp32 residual stream
 //   xn = LayerNorm(x) * ln_gamma + ln_beta      -> activation type (next GEMM's A operand)
 // Saves one pass over the fp32 stream and one launch per stage.
-template <typename T, bool PRECISE, int NCH>
-__global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, int M, int group_ch,
+template <typename T, bool PRECISE, int NCH, typename HT = float>
+__global__ void gn_apply_ln_kernel(const HT* __restrict__ h, long long ld_h, int M, int group_ch,
                                    const int* __restrict__ row_info, const double* __restrict__ stats,
                                    const double* __restrict__ bias_gsum, const UttTable* __restrict__ utt,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ resid, long long ld_resid, float* __restrict__ out_f32,
+                                   const HT* __restrict__ resid, long long ld_resid, float* __restrict__ out_f32,
                                    long long ld_f32, const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
                                    T* __restrict__ out_ln, long long ld_ln) {
   constexpr int C = NCH * 128;
@@ -258,9 +271,9 @@ __global__ void gn_apply_ln_kernel(const float* __restrict__ h, long long ld_h, 
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = i * 128 + lane * 4;
-    const float4 r = *reinterpret_cast<const float4*>(resid + (long long)row * ld_resid + c);
+    const float4 r = ld4(resid + (long long)row * ld_resid + c);
     y[i][0] = r.x, y[i][1] = r.y, y[i][2] = r.z, y[i][3] = r.w;
-    const float4 hv = *reinterpret_cast<const float4*>(h + (long long)row * ld_h + c);  // unconditional: overlaps the flag load
+    const float4 hv = ld4(h + (long long)row * ld_h + c);  // unconditional: overlaps the flag load
     if (valid) {
       const float2 st = gn_mean_rstd(stats, bias_gsum, utt, b, c / group_ch);
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
