@@ -598,11 +598,12 @@ __device__ __forceinline__ void epi_block_wide(const GemmParams& p, uint32_t stg
 // I/O so TMEM latency overlaps it.  Shared by the 1-CTA and the CTA-pair kernels.
 template <int BN, int MODE, int EPI_LD, int N_EPI_WARPS>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, uint32_t stg, int m0, int n0, int ewarp, int lane,
-                                              int acc, uint32_t gn_slots, uint32_t gn_counters) {
+                                              int acc, uint32_t gn_slots, uint32_t gn_counters, int info_pre = -1) {
   const int half = ewarp >> 2;
   const int q = ewarp & 3;
-  // STORE / SNAKE never look at the row flags: skip the (L2-latency) load that would sit on the tile's critical path
-  const int info = (MODE == EPI_STORE || MODE == EPI_SNAKE) ? ROW_VALID : load_row_info(p, m0 + lane);
+  // STORE / SNAKE never look at the row flags; the other modes get them from the caller, which requests them before it waits
+  // for the accumulator (info_pre >= 0), so that their L2 latency does not open the tile's epilogue
+  const int info = (MODE == EPI_STORE || MODE == EPI_SNAKE) ? ROW_VALID : (info_pre >= 0 ? info_pre : load_row_info(p, m0 + lane));
   const uint32_t valid_mask = __ballot_sync(0xffffffffu, (info & ROW_VALID) != 0);
   const uint32_t instat_mask = __ballot_sync(0xffffffffu, (info & ROW_INSTAT) != 0);
   bool do_stats = false, uniform = false;
@@ -813,11 +814,11 @@ __device__ __forceinline__ void stg256(void* dst, const uint32_t (&v)[8]) {
 }
 template <int BN, int MODE, typename Release>
 __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32_t taddr, int m0, int n0, int half, int lane,
-                                                     Release&& release) {
+                                                     Release&& release, int info_pre = -1) {
   constexpr int UNITS = BN / 32;
   const int m = m0 + lane;
   bool valid = true;
-  if constexpr (MODE == EPI_MASK) valid = (load_row_info(p, m) & ROW_VALID) != 0;
+  if constexpr (MODE == EPI_MASK) valid = ((info_pre >= 0 ? info_pre : load_row_info(p, m)) & ROW_VALID) != 0;
   bf16* orow = reinterpret_cast<bf16*>(p.out_act) + (long long)m * p.ld_act;
   uint32_t ra[16], rb[16];
   bool released = false;
@@ -1191,7 +1192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t acc_phase = (local >> 1) & 1;
         const int m0 = ((tile / n_tiles) * CL + crank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
         int info_pre = 0;  // row flags requested before the accumulator wait: their latency hides under the MMAs of this tile
-        if constexpr (MODE == EPI_STATS16) info_pre = load_row_info(p, m0 + lane);
+        if constexpr (MODE != EPI_STORE && MODE != EPI_SNAKE) info_pre = load_row_info(p, m0 + lane);
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -1209,7 +1210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-            });
+            }, info_pre);
             continue;
           }
         }
@@ -1223,7 +1224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             continue;
           }
         }
-        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
+        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters, info_pre);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -1414,7 +1415,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t acc_phase = (local >> 1) & 1;
         const int m0 = ((tile / n_tiles) * 2 + rank) * Cfg::BM + q * 32, n0 = (tile % n_tiles) * BN;
         int info_pre = 0;  // row flags requested before the accumulator wait: their latency hides under the MMAs of this tile
-        if constexpr (MODE == EPI_STATS16) info_pre = load_row_info(p, m0 + lane);
+        if constexpr (MODE != EPI_STORE && MODE != EPI_SNAKE) info_pre = load_row_info(p, m0 + lane);
         mbar_wait_prof(&tfull_bar[acc], acc_phase, prof, w_tfull);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -1438,7 +1439,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 if (rank == 0) ptx::mbar_arrive(&tempty_bar[acc]);
                 else ptx::mbar_arrive_remote_relaxed(&tempty_bar[acc], 0);
               }
-            });
+            }, info_pre);
             continue;
           }
         }
@@ -1455,7 +1456,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             continue;
           }
         }
-        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters);
+        epilogue_tile<BN, MODE, Cfg::EPI_LD, Cfg::N_EPI_WARPS>(p, taddr, stg, m0, n0, warp - 4, lane, acc, gn_slots, gn_counters, info_pre);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {  // the accumulator of BOTH CTAs must be drained before the leader's MMA thread reuses it
