@@ -120,6 +120,10 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *   "ff_fused"    0/1: FeedForward (Linear -> SnakeBeta -> Linear + residual) as ONE kernel with the 4C hidden kept in tensor memory
  *                 (csrc/ff_fused.cuh) instead of two GEMMs through a [rows, 4C] HBM buffer; plans above "small_tiles" rows only
  *                 (default 0: measured slower)
+ *   "rowln"       0/1/2: Linear + residual add + LayerNorm as ONE kernel (csrc/rowln.cuh: a CTA owns whole 128 x C row tiles) for
+ *                 out-proj -> norm3 and FF2 -> next block's norm1: off / plans above "small_tiles" rows / always; C % 128 == 0 only
+ *                 (default 0: measured equal or slower, header of rowln.cuh); "rowln_ff2" 0/1 excludes / includes the FF2 site
+ *   "bf16_mid"    0/1: conv / res_conv outputs stored as bf16, statistics from the fp32 accumulators (default 1)
  *   "bn_full" / "bn_half" / "pair_min_k": tile-shape experiments for the N = C GEMMs (0 = automatic)
  *   "plan_cache"  n: plans (row tables + workspace + CUDA graph) kept per handle, least recently used evicted (default 8);
  *                 the only option that does not drop the cached plans */
@@ -189,6 +193,11 @@ int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev);
  * [16] total [7] waiting for P (epilogue) [8] W2 [9] Y drained; epilogue warp [10] total [11] waiting for H [12] waiting for Y
  * [13] residual update; [15] tiles of CTA 0. */
 int cfm_debug_ff_profile(cfm_handle* h, unsigned long long* prof_dev);
+/* Debug: every later gemm_rowln_kernel launch (direct launches only) writes CTA 0's cycle counters to prof_dev[0..16): producer
+ * [0] total [1] waiting for free stages; MMA warp [2] total [3] waiting for operands [4] waiting for the drained accumulator;
+ * epilogue warp [5] total [6] waiting for the accumulator [7] pass 1 (residual add + statistics) [8] exchange [9] pass 2 (normalise)
+ * [10] tiles of CTA 0. */
+int cfm_debug_rowln_profile(cfm_handle* h, unsigned long long* prof_dev);
 /* Debug: tensor-core GEMM in one epilogue mode (0 bf16 store, 1 fp32 store, 2 fp32 in-place residual add) with per-role
  * cycle counters of CTA 0 written to prof[0..16) (device memory); see csrc/cfm.cu for the slot meanings. */
 int cfm_debug_gemm_profile(cfm_handle* h, const void* a_bf16, const void* w_bf16, float* d_f32, void* d_bf16, int32_t M,

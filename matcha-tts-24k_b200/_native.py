@@ -12,7 +12,7 @@ SOLVERS = {"euler": 0, "midpoint": 1, "heun3": 2, "rk4": 3}
 FLAG_NO_GRAPH, FLAG_SIMT_GEMM, FLAG_UNFUSED_STATS, FLAG_SIMT_ATTN = 1, 2, 4, 8
 EXPORTS = ["cfm_create", "cfm_destroy", "cfm_last_error", "cfm_load_weights", "cfm_plan", "cfm_solve", "cfm_solve_host",
            "cfm_estimator", "cfm_plan_info", "cfm_debug_read", "cfm_debug_gemm", "cfm_debug_stop_after", "cfm_debug_gemm_profile", "cfm_debug_attn_profile", "cfm_set_speakers", "cfm_set_lanes", "cfm_set_option",
-           "cfm_solve_host_spks", "cfm_estimator_t", "cfm_debug_timeline", "cfm_debug_ff_profile", "cfm_solve_host_indexed", "cfm_synchronize",
+           "cfm_solve_host_spks", "cfm_estimator_t", "cfm_debug_timeline", "cfm_debug_ff_profile", "cfm_debug_rowln_profile", "cfm_solve_host_indexed", "cfm_synchronize",
            "cfm_front_durations", "cfm_front_expand", "cfm_denormalize"]
 
 
@@ -62,6 +62,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.cfm_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.cfm_debug_attn_profile.argtypes = [vp, vp]
     lib.cfm_debug_ff_profile.argtypes = [vp, vp]
+    lib.cfm_debug_rowln_profile.argtypes = [vp, vp]
     lib.cfm_solve_host_indexed.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i32), i32]
     lib.cfm_synchronize.argtypes = [vp]
     lib.cfm_front_durations.argtypes = [vp, vp, i32, i32, vp, vp, vp]

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libcfm_b200.so")
-HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", "attn.cuh", "attn_tc.cuh", "ff_fused.cuh", os.path.join("..", "..", "include", "cfm_b200.h")]
+HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", "attn.cuh", "attn_tc.cuh", "ff_fused.cuh", "rowln.cuh", os.path.join("..", "..", "include", "cfm_b200.h")]
 TC = [(64, 8), (128, 8), (160, 8), (192, 8), (256, 8), (256, 12)]  # gemm_tc_kernel<BN, epilogue warps>  (gemm.cuh CFM_FOR_EACH_TC)
 TC2 = [128, 160, 192, 256]                                          # gemm_tc2_kernel<BN>                  (CFM_FOR_EACH_TC2)
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -27,7 +27,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
 
 def units():
     """(object name, source, extra defines)"""
-    out = [("cfm.o", "cfm.cu", []), ("attn_inst.o", "attn_inst.cu", []), ("ff_inst.o", "ff_inst.cu", [])]
+    out = [("cfm.o", "cfm.cu", []), ("attn_inst.o", "attn_inst.cu", []), ("ff_inst.o", "ff_inst.cu", []), ("rowln_inst.o", "rowln_inst.cu", [])]
     out += [(f"gemm_tc_{bn}_{new}.o", "gemm_inst.cu", [f"-DCFM_BN={bn}", f"-DCFM_NEW={new}", "-DCFM_PAIR=0"]) for bn, new in TC]
     out += [(f"attn_simt_{bf}_{d}.o", "attn_simt_inst.cu", [f"-DCFM_BF16={bf}", f"-DCFM_D={d}"]) for bf in (0, 1) for d in (32, 64)]
     out += [(f"gemm_tc2_{bn}.o", "gemm_inst.cu", [f"-DCFM_BN={bn}", "-DCFM_NEW=8", "-DCFM_PAIR=1"]) for bn in TC2]

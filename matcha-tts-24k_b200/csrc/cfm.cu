@@ -20,6 +20,7 @@
 #include "attn.cuh"
 #include "attn_tc.cuh"
 #include "ff_fused.cuh"
+#include "rowln.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -162,6 +163,10 @@ struct cfm_handle {
   int bf16_mid = 1;                             // tensor-core mode: the conv output between a conv and its GroupNorm-apply and the
                                                 // res_conv output are stored as bf16 (statistics still come from the fp32
                                                 // accumulators), written by row-per-thread epilogues without smem staging; "bf16_mid"
+  int rowln = 0;                                // Linear + residual + LayerNorm in one kernel (rowln.cuh) for out-proj -> norm3 and FF2 -> next
+                                                // block's norm1: 0 off, 1 for plans above `small_tiles` rows, 2 always; "rowln".
+  int rowln_ff2 = 1;                            // also fuse FF2 -> next norm1 (K = 4C); "rowln_ff2".
+  unsigned long long* rowln_prof = nullptr;     // debug: device buffer for gemm_rowln_kernel's CTA-0 cycle counters
   int ff_fused = 0;                             // FF1 -> SnakeBeta -> FF2 in one kernel (ff_fused.cuh) for plans above `small_tiles` rows; "ff_fused".
                                                 // Off by default: correct, removes the [rows, 4C] round trip through HBM, but measured
                                                 // 108 / 63 us per full / half resolution block against 96 / 58 us for the two GEMMs
@@ -627,6 +632,10 @@ int set_gemm_attrs(cfm_handle* h) {
     const KernelInfo k = kinfo_ff_fused();
     CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
   }
+  {
+    const KernelInfo k = kinfo_rowln();
+    CK(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+  }
   const KernelInfo k = tc_info(192, 8);  // co-resident cluster capacity (1 CTA per SM): bounds the persistent grid
   for (int CL = 1; CL <= 4; CL *= 2) {
     cudaLaunchConfig_t cfg;
@@ -958,10 +967,64 @@ int run_ff_fused(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, l
   return 0;
 }
 
+// Linear + residual add + LayerNorm as one kernel (rowln.cuh): X += A . W^T + b, Xn = LayerNorm(X) gamma + beta.
+bool rowln_ok(cfm_handle* h, const Res& R) {
+  const int C = h->C();
+  const bool tc = h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  return tc && C % 128 == 0 && C <= RowLnCfg::MAX_N && (h->rowln == 2 || (h->rowln == 1 && R.M > h->small_tiles));
+}
+int run_rowln(cfm_handle* h, const Res& R, const void* A, long long lda, const GemmW& w, const NormW& ln, const char* tag, cudaStream_t s) {
+  if (h->stopped()) return 0;
+  h->launch_counter++;
+  const int C = h->C();
+  CKR(tl_mark(h, s, tag, R.M, C, w.Kp, 2.0 * R.M * C * w.Kp));
+  CUtensorMap tmA, tmW, tmX, tmN;
+  CKR(make_tmap(h, &tmA, A, w.Kp, R.M, lda * 2, 64, 128));
+  CKR(make_tmap(h, &tmW, w.w, w.Kp, w.n_stride, (long long)w.Kp * 2, 64, C / 2));
+  CKR(make_out_tmap(h, &tmX, R.X, true, C, R.M, C));
+  CKR(make_out_tmap(h, &tmN, R.Xn, false, C, R.M, C));
+  RowLnParams p;
+  memset(&p, 0, sizeof p);
+  p.M = R.M, p.N = C, p.K = w.Kp;
+  p.bias = w.bias, p.gamma = ln.gamma, p.beta = ln.beta;
+  p.X = R.X, p.ldx = C, p.Xn = static_cast<bf16*>(R.Xn), p.ldn = C, p.eps = 1e-5f;
+  p.prof = h->rowln_prof;
+  const KernelInfo k = kinfo_rowln();
+  const int m_tiles = (R.M + RowLnCfg::BM - 1) / RowLnCfg::BM;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(std::min(m_tiles, h->max_clusters[1])), cfg.blockDim = dim3(k.threads), cfg.dynamicSmemBytes = RowLnCfg::smem_bytes(C), cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (h->win_bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = h->win_ptr;
+    attr[n].val.accessPolicyWindow.num_bytes = h->win_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
+  if (h->pdl_now) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  void* args[] = {&tmA, &tmW, &tmX, &tmN, &p};
+  CK(cudaLaunchKernelExC(&cfg, k.fn, args));
+  return 0;
+}
+
 // BasicTransformerBlock (reference transformer.py:230-303).  If copy_dst != nullptr the FF2 epilogue also writes the
 // masked activation-type copy of the block output there (skip connection / next conv input).
-int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s, bool ln1_done) {
+// next_ln1: norm1 of the transformer block that follows in the same stack (nullptr for the last one); *next_ln1_done is set when
+// this block's FF2 launch has already produced it.
+int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long long copy_ld, cudaStream_t s, bool ln1_done,
+              const NormW* next_ln1 = nullptr, bool* next_ln1_done = nullptr) {
   const int C = h->C(), I = h->inner();
+  const bool fuse_ln = rowln_ok(h, R) && I % 64 == 0;
+  if (next_ln1_done) *next_ln1_done = false;
   if (!ln1_done) CKR(run_layernorm(h, R, w.ln1, s));
   {
     GemmParams p = gemm_base(R.M, R.Xn, C, R.M, w.qkv, nullptr, nullptr);
@@ -970,13 +1033,15 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
     CKR(launch_gemm(h, p, true, s));
   }
   CKR(run_attention(h, R, s));
-  {
+  if (fuse_ln) {
+    CKR(run_rowln(h, R, R.ao, I, w.out, w.ln3, "out_proj_ln", s));
+  } else {
     GemmParams p = gemm_base(R.M, R.ao, I, R.M, w.out, nullptr, nullptr);
     p.mode = EPI_RESID, p.resid = R.X, p.ld_resid = C, p.out_f32 = R.X, p.ld_f32 = C;
     h->tag = "out_proj";
     CKR(launch_gemm(h, p, true, s));
+    CKR(run_layernorm(h, R, w.ln3, s));
   }
-  CKR(run_layernorm(h, R, w.ln3, s));
   const bool tc = h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
   if (tc && h->ff_fused && C % 64 == 0 && C <= FfCfg::MAX_C && R.M > h->small_tiles) return run_ff_fused(h, R, w, copy_dst, copy_ld, s);
   {
@@ -984,6 +1049,11 @@ int run_block(cfm_handle* h, const Res& R, const BlockW& w, void* copy_dst, long
     p.mode = EPI_SNAKE, p.ea = w.ea, p.ib = w.ib, p.out_act = R.ffh, p.ld_act = 4 * C;
     h->tag = "ff1_snake";
     CKR(launch_gemm(h, p, true, s));
+  }
+  if (fuse_ln && next_ln1 && !copy_dst && (h->rowln_ff2 != 0)) {
+    CKR(run_rowln(h, R, R.ffh, 4 * C, w.ff2, *next_ln1, "ff2_ln", s));
+    if (next_ln1_done) *next_ln1_done = true;
+    return 0;
   }
   {
     GemmParams p = gemm_base(R.M, R.ffh, 4 * C, R.M, w.ff2, nullptr, nullptr);
@@ -1004,9 +1074,12 @@ int run_stage(cfm_handle* h, Plan* pl, const Res& R, const StageW& w, const void
   // the resnet's last GroupNorm-apply also produces LayerNorm1 of the first transformer block when the width allows
   const bool fuse = h->C() % 128 == 0 && h->C() <= 512 && !w.blocks.empty() && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS);
   CKR(run_resnet(h, pl, R, w.res, A, lda, site, tproj, tproj_stride, s, fuse ? &w.blocks[0].ln1 : nullptr));
+  bool ln1_done = fuse;
   for (size_t j = 0; j < w.blocks.size(); ++j) {
     const bool last = j + 1 == w.blocks.size();
-    CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s, fuse && j == 0));
+    bool next_done = false;
+    CKR(run_block(h, R, w.blocks[j], last ? copy_dst : nullptr, copy_ld, s, ln1_done, last ? nullptr : &w.blocks[j + 1].ln1, &next_done));
+    ln1_done = next_done;
   }
   return 0;
 }
@@ -1905,6 +1978,8 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "l2_persist_mb") == 0 && value >= 0) return apply_l2_persist(h, value);
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
+  else if (strcmp(key, "rowln") == 0 && value >= 0 && value <= 2) h->rowln = value;
+  else if (strcmp(key, "rowln_ff2") == 0) h->rowln_ff2 = value != 0;
   else if (strcmp(key, "bf16_mid") == 0) h->bf16_mid = value != 0;
   else if (strcmp(key, "bn_full") == 0) h->bn_full = value;
   else if (strcmp(key, "bn_half") == 0) h->bn_half = value;
@@ -1925,6 +2000,12 @@ int cfm_debug_attn_profile(cfm_handle* h, unsigned long long* prof_dev) {
 int cfm_debug_ff_profile(cfm_handle* h, unsigned long long* prof_dev) {
   if (!h) return CFM_ERR_INVALID;
   h->ff_prof = prof_dev;
+  return 0;
+}
+
+int cfm_debug_rowln_profile(cfm_handle* h, unsigned long long* prof_dev) {
+  if (!h) return CFM_ERR_INVALID;
+  h->rowln_prof = prof_dev;
   return 0;
 }
 

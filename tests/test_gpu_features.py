@@ -168,6 +168,26 @@ def test_fused_feed_forward_kernel_matches_two_gemm_schedule(dec, lengths):
     m.close()
 
 
+@pytest.mark.parametrize("dec,lengths", [(syn.PROD, [300, 171, 64, 1]), (SMALL, [150, 97])])
+def test_fused_linear_layernorm_kernel_matches_unfused_schedule(dec, lengths):
+    """rowln.cuh (out-proj / FF2 + residual add + the following LayerNorm in one kernel, whole rows per CTA) against the default
+    schedule and the oracle: solve x2, bf16 tolerance; "rowln" 2 sends every resolution through the fused kernel."""
+    ora, m = pair(dec, precision="bf16")
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=62)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    outs = {}
+    m.refresh(torch.device("cuda", 0))
+    for fused in (0, 2):
+        m.set_option("rowln", fused)
+        outs[fused] = m.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+        err = rel_l2(outs[fused], ref)
+        print(f"rowln={fused}: rel_l2 vs oracle {err:.3e}")
+        assert err <= 1e-2
+    assert rel_l2(outs[2], outs[0]) <= 1e-2
+    m.close()
+
+
 def _sharded_case(devices):
     lengths = [120, 64, 97, 33, 150, 88, 140]
     ora, single = pair(SMALL, precision="fp32")
