@@ -27,7 +27,12 @@ typedef enum {
   CFM_ERR_WEIGHTS = -4    /* missing, unexpected or mis-shaped parameter */
 } cfm_status;
 
-typedef enum { CFM_PREC_BF16 = 0, CFM_PREC_FP32 = 1 } cfm_precision;
+/* BF16: bf16 operands on the tensor pipe, fp32 accumulation / residual stream / statistics / ODE state (the speed mode).
+ * FP32: fp32 storage and fp32-FMA kernels everywhere (the parity reference, ~1e-6 of the oracle).
+ * FP32_TC: fp32 storage, GEMMs and attention on the bf16 tensor pipe with bf16 x 3 split operands (a = hi + lo; hi*hi + lo*hi +
+ *          hi*lo, fp32 accumulation): ~1-2e-5 relative L2 of the oracle, ~9x faster than FP32 (cfm_set_option "fp32_tc" toggles
+ *          it on an FP32 handle). */
+typedef enum { CFM_PREC_BF16 = 0, CFM_PREC_FP32 = 1, CFM_PREC_FP32_TC = 2 } cfm_precision;
 typedef enum { CFM_SOLVER_EULER = 0, CFM_SOLVER_MIDPOINT = 1, CFM_SOLVER_HEUN3 = 2, CFM_SOLVER_RK4 = 3 } cfm_solver;
 
 /* Mirrors the keyword arguments of the reference estimator constructor
@@ -123,6 +128,7 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *   "rowln"       0/1/2: Linear + residual add + LayerNorm as ONE kernel (csrc/rowln.cuh: a CTA owns whole 128 x C row tiles) for
  *                 out-proj -> norm3 and FF2 -> next block's norm1: off / plans above "small_tiles" rows / always; C % 128 == 0 only
  *                 (default 0: measured equal or slower, header of rowln.cuh); "rowln_ff2" 0/1 excludes / includes the FF2 site
+ *   "fp32_tc"     0/1 (fp32 handles): GEMMs and attention on the tensor pipe with bf16 x 3 split operands (CFM_PREC_FP32_TC sets it)
  *   "bf16_mid"    0/1: conv / res_conv outputs stored as bf16, statistics from the fp32 accumulators (default 1)
  *   "bn_full" / "bn_half" / "pair_min_k": tile-shape experiments for the N = C GEMMs (0 = automatic)
  *   "plan_cache"  n: plans (row tables + workspace + CUDA graph) kept per handle, least recently used evicted (default 8);

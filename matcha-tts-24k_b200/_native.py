@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcfm_b200.so")
 
-PREC = {"bf16": 0, "fp32": 1}
+PREC = {"bf16": 0, "fp32": 1, "fp32_tc": 2}
 SOLVERS = {"euler": 0, "midpoint": 1, "heun3": 2, "rk4": 3}
 FLAG_NO_GRAPH, FLAG_SIMT_GEMM, FLAG_UNFUSED_STATS, FLAG_SIMT_ATTN = 1, 2, 4, 8
 EXPORTS = ["cfm_create", "cfm_destroy", "cfm_last_error", "cfm_load_weights", "cfm_plan", "cfm_solve", "cfm_solve_host",

@@ -22,16 +22,22 @@
 
 namespace cfm {
 
-struct AttnTcCfg {
-  static constexpr int D = 64, QT = 128, KT = 64;
+// X3: fp32 in / out on the bf16 tensor pipe - every operand tile exists twice, hi = bf16(x) and lo = bf16(x - hi) (the caller
+// hands a [hi | lo] copy of the QKV buffer, kernels.cuh split3_rows_kernel), S = Qh Kh^T + Ql Kh^T + Qh Kl^T and
+// O += Ph Vh + Pl Vh + Ph Vl with fp32 accumulation (dropped terms ~2^-17 relative); softmax, row sums and output in fp32.
+template <bool X3>
+struct AttnTcCfgT {
+  static constexpr int D = 64, QT = 128, KT = 64, NP = X3 ? 2 : 1;  // NP: tiles per operand (hi, lo)
   static constexpr int Q_BYTES = QT * D * 2, K_BYTES = KT * D * 2, V_BYTES = KT * D * 2, P_BYTES = QT * KT * 2;
-  static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + 2 * K_BYTES, OFF_P = OFF_V + 2 * V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;  // 11 mbarriers + TMEM slot (128 B)
+  static constexpr int OFF_Q = 0, OFF_K = NP * Q_BYTES, OFF_V = OFF_K + 2 * NP * K_BYTES, OFF_P = OFF_V + 2 * NP * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * NP * P_BYTES;  // 11 mbarriers + TMEM slot (128 B)
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
   static constexpr int N_SOFTMAX_WARPS = 4;
   static constexpr int THREADS = 64 + 32 * N_SOFTMAX_WARPS;
   static constexpr int TMEM_COLS = 256;  // S[2] at columns 0 / 64, PV at column 128
+  static constexpr int MIN_CTAS = X3 ? 1 : 2;
 };
+using AttnTcCfg = AttnTcCfgT<false>;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -70,11 +76,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 #ifdef CFM_ATTN_KERNEL_TU  // the kernel body is compiled only in attn_inst.cu; cfm.cu launches through kinfo_attn_tc()
-__global__ void __launch_bounds__(AttnTcCfg::THREADS, 2)
+template <bool X3>
+__global__ void __launch_bounds__(AttnTcCfgT<X3>::THREADS, AttnTcCfgT<X3>::MIN_CTAS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int inner,
-               const UttTable* __restrict__ utt, const int4* __restrict__ work, bf16* __restrict__ out, long long ldo,
+               const UttTable* __restrict__ utt, const int4* __restrict__ work, void* __restrict__ out_v, long long ldo,
                float scale_log2, unsigned long long* prof) {
-  using Cfg = AttnTcCfg;
+  using Cfg = AttnTcCfgT<X3>;
+  constexpr int NP = Cfg::NP;
+  const int lo_col = 3 * inner;  // X3: first column of the lo parts in the [hi | lo] QKV copy
   const bool do_prof = prof != nullptr && blockIdx.x == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,13 +115,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     // Q and the first two K / V tiles are requested right away: their L2 latency overlaps the TMEM allocation and the
     // CTA-wide barrier below instead of following them (the barriers they complete on are initialised and fenced above).
     ptx::pdl_wait();
-    ptx::mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-    ptx::tma_load_2d(smem + Cfg::OFF_Q, &tm_q, bar_q, head * Cfg::D, row0 + q0);
+    ptx::mbar_expect_tx(bar_q, NP * Cfg::Q_BYTES);
+    for (int pt = 0; pt < NP; ++pt) ptx::tma_load_2d(smem + Cfg::OFF_Q + pt * Cfg::Q_BYTES, &tm_q, bar_q, pt * lo_col + head * Cfg::D, row0 + q0);
     for (int j = 0; j < 2 && j < n_tiles; ++j) {
-      ptx::mbar_expect_tx(bar_k + j, Cfg::K_BYTES);
-      ptx::tma_load_2d(smem + Cfg::OFF_K + j * Cfg::K_BYTES, &tm_kv, bar_k + j, inner + head * Cfg::D, row0 + j * Cfg::KT);
-      ptx::mbar_expect_tx(bar_v + j, Cfg::V_BYTES);
-      ptx::tma_load_2d(smem + Cfg::OFF_V + j * Cfg::V_BYTES, &tm_kv, bar_v + j, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+      ptx::mbar_expect_tx(bar_k + j, NP * Cfg::K_BYTES);
+      ptx::mbar_expect_tx(bar_v + j, NP * Cfg::V_BYTES);
+      for (int pt = 0; pt < NP; ++pt) {
+        ptx::tma_load_2d(smem + Cfg::OFF_K + (j * NP + pt) * Cfg::K_BYTES, &tm_kv, bar_k + j, pt * lo_col + inner + head * Cfg::D, row0 + j * Cfg::KT);
+        ptx::tma_load_2d(smem + Cfg::OFF_V + (j * NP + pt) * Cfg::V_BYTES, &tm_kv, bar_v + j, pt * lo_col + 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+      }
     }
   }
   if (warp == 1) {
@@ -136,11 +147,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int b = j & 1;
         const uint32_t prev = ((j >> 1) - 1) & 1;  // parity of the previous use of buffer b
         ptx::mbar_wait(bar_s + b, prev);  // S_{j-2} complete: K[b] free
-        ptx::mbar_expect_tx_elect(bar_k + b, Cfg::K_BYTES);
-        ptx::tma_load_2d_elect(smem + Cfg::OFF_K + b * Cfg::K_BYTES, &tm_kv, bar_k + b, inner + head * Cfg::D, row0 + j * Cfg::KT);
+        ptx::mbar_expect_tx_elect(bar_k + b, NP * Cfg::K_BYTES);
+        for (int pt = 0; pt < NP; ++pt)
+          ptx::tma_load_2d_elect(smem + Cfg::OFF_K + (b * NP + pt) * Cfg::K_BYTES, &tm_kv, bar_k + b, pt * lo_col + inner + head * Cfg::D, row0 + j * Cfg::KT);
         ptx::mbar_wait(bar_pv + b, prev);  // PV_{j-2} complete: V[b] free
-        ptx::mbar_expect_tx_elect(bar_v + b, Cfg::V_BYTES);
-        ptx::tma_load_2d_elect(smem + Cfg::OFF_V + b * Cfg::V_BYTES, &tm_kv, bar_v + b, 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
+        ptx::mbar_expect_tx_elect(bar_v + b, NP * Cfg::V_BYTES);
+        for (int pt = 0; pt < NP; ++pt)
+          ptx::tma_load_2d_elect(smem + Cfg::OFF_V + (b * NP + pt) * Cfg::V_BYTES, &tm_kv, bar_v + b, pt * lo_col + 2 * inner + head * Cfg::D, row0 + j * Cfg::KT);
       }
     }
   } else if (warp == 1) {
@@ -156,9 +169,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_wait_prof(bar_k + b, (j >> 1) & 1, do_prof, wk);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_elect(tmem_base + b * 64, ptx::umma_desc_sw128(q_addr + k * 32),
-                         ptx::umma_desc_sw128(k_addr + b * Cfg::K_BYTES + k * 32), idesc_s, k > 0);
+        for (int pr = 0; pr < (X3 ? 3 : 1); ++pr) {  // (Q part, K part): hi hi, lo hi, hi lo
+          const uint32_t qa = q_addr + (pr == 1 ? Cfg::Q_BYTES : 0), ka = k_addr + (b * NP + (pr == 2 ? 1 : 0)) * Cfg::K_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_elect(tmem_base + b * 64, ptx::umma_desc_sw128(qa + k * 32), ptx::umma_desc_sw128(ka + k * 32), idesc_s, (pr > 0 || k > 0) ? 1u : 0u);
+        }
         ptx::umma_commit_elect(bar_s + b);
       };
       mbar_wait_prof(bar_q, 0, do_prof, wq);
@@ -171,9 +187,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_wait_prof(bar_v + b, ph, do_prof, wv);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_elect(tmem_pv, ptx::umma_desc_sw128(p_addr + b * Cfg::P_BYTES + k * 32),
-                         ptx::umma_desc_sw128(v_addr + b * Cfg::V_BYTES + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        for (int pr = 0; pr < (X3 ? 3 : 1); ++pr) {  // (P part, V part): hi hi, lo hi, hi lo
+          const uint32_t pa = p_addr + (b * NP + (pr == 1 ? 1 : 0)) * Cfg::P_BYTES, va = v_addr + (b * NP + (pr == 2 ? 1 : 0)) * Cfg::V_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_elect(tmem_pv, ptx::umma_desc_sw128(pa + k * 32), ptx::umma_desc_sw128(va + k * 2048), idesc_pv, (j > 0 || pr > 0 || k > 0) ? 1u : 0u);
+        }
         ptx::umma_commit_elect(bar_pv + b);
         if (j + 2 < n_tiles) issue_s(j + 2);
       }
@@ -205,7 +224,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       const int k0 = j * Cfg::KT;
-      const uint32_t p_row = ptx::smem_u32(smem + Cfg::OFF_P + b * Cfg::P_BYTES + r * 128);
+      const uint32_t p_row = ptx::smem_u32(smem + Cfg::OFF_P + b * NP * Cfg::P_BYTES + r * 128);
       ptx::tmem_ld_wait();
       if (k0 + Cfg::KT > L) {  // tile holds the pad token and / or rows past this utterance: fix the raw scores in place
 #pragma unroll
@@ -262,6 +281,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
           ptx::sts128_u32(p_row + ((g ^ (r & 7)) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                           *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          if constexpr (X3) {  // lo part of P: what bf16 rounding dropped
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1), f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+            __nv_bfloat162 l0 = __floats2bfloat162_rn(pv[0] - f0.x, pv[1] - f0.y), l1 = __floats2bfloat162_rn(pv[2] - f1.x, pv[3] - f1.y);
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(pv[4] - f2.x, pv[5] - f2.y), l3 = __floats2bfloat162_rn(pv[6] - f3.x, pv[7] - f3.y);
+            ptx::sts128_u32(p_row + Cfg::P_BYTES + ((g ^ (r & 7)) << 4), *reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
+                            *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
+          }
         }
         float s0, s1;
         unpack2(add2(acc01, acc23), s0, s1);
@@ -281,12 +307,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (sp && lane == 0) prof[8] = (unsigned long long)(clock64() - ts_start), prof[9] = ws, prof[10] = wbar, prof[11] = wpv;
     const int qi = q0 + r;
     const float inv = 1.f / lrun;
-    bf16* dst = out + (long long)(row0 + qi) * ldo + head * Cfg::D;
+    bf16* dst = static_cast<bf16*>(out_v) + (long long)(row0 + qi) * ldo + head * Cfg::D;
+    float* dst_f = static_cast<float*>(out_v) + (long long)(row0 + qi) * ldo + head * Cfg::D;
 #pragma unroll
     for (int c = 0; c < 64; c += 16) {
       uint32_t a[16];
       ptx::tmem_ld16(tmem_pv + lane_off + c, a);
       ptx::tmem_ld_wait();
+      if constexpr (X3) {
+        if (qi < nk) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(dst_f + c + 4 * g) = make_float4(__uint_as_float(a[4 * g]) * inv, __uint_as_float(a[4 * g + 1]) * inv,
+                                                                        __uint_as_float(a[4 * g + 2]) * inv, __uint_as_float(a[4 * g + 3]) * inv);
+        }
+        continue;
+      }
       if (qi < nk) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -311,14 +347,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   }
 }
 
-KernelInfo kinfo_attn_tc() { return KernelInfo{reinterpret_cast<const void*>(&attn_tc_kernel), AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES}; }
+KernelInfo kinfo_attn_tc(int x3) {
+  if (x3) return KernelInfo{reinterpret_cast<const void*>(&attn_tc_kernel<true>), AttnTcCfgT<true>::THREADS, AttnTcCfgT<true>::SMEM_BYTES};
+  return KernelInfo{reinterpret_cast<const void*>(&attn_tc_kernel<false>), AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES};
+}
 #else
 
 inline int attn_tc_set_attr(std::string* err) {
-  cudaError_t e = cudaFuncSetAttribute(kinfo_attn_tc().fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
-  if (e != cudaSuccess) {
-    *err = std::string("cudaFuncSetAttribute(attn_tc_kernel): ") + cudaGetErrorString(e);
-    return -2;
+  for (int x3 = 0; x3 < 2; ++x3) {
+    const KernelInfo k = kinfo_attn_tc(x3);
+    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaFuncSetAttribute(attn_tc_kernel): ") + cudaGetErrorString(e);
+      return -2;
+    }
   }
   return 0;
 }
@@ -326,10 +368,11 @@ inline int attn_tc_set_attr(std::string* err) {
 template <typename Enc>
 inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, int M, const UttTable* utt, const int4* work,
                           int n_work, void* out, long long ldo, float scale, cudaStream_t s, std::string* err,
-                          unsigned long long* prof = nullptr, bool pdl = false) {
+                          unsigned long long* prof = nullptr, bool pdl = false, bool x3 = false) {
+  // x3: qkv is the bf16 [hi | lo] copy ([M, 2 ld], lo parts at column ld) of an fp32 QKV buffer, out is fp32
   CUtensorMap tm_q, tm_kv;
-  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t dims[2] = {(cuuint64_t)ld * (x3 ? 2 : 1), (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2 * (x3 ? 2 : 1)};
   cuuint32_t estr[2] = {1, 1};
   for (int i = 0; i < 2; ++i) {
     cuuint32_t box[2] = {64, (cuuint32_t)(i == 0 ? AttnTcCfg::QT : AttnTcCfg::KT)};
@@ -343,15 +386,16 @@ inline int launch_attn_tc(Enc encode, const void* qkv, long long ld, int inner, 
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(n_work), cfg.blockDim = dim3(AttnTcCfg::THREADS), cfg.dynamicSmemBytes = AttnTcCfg::SMEM_BYTES, cfg.stream = s;
+  const KernelInfo ki = kinfo_attn_tc(x3 ? 1 : 0);
+  cfg.gridDim = dim3(n_work), cfg.blockDim = dim3(ki.threads), cfg.dynamicSmemBytes = ki.smem, cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
-  bf16* out_b = static_cast<bf16*>(out);
+  void* out_b = out;
   float scale_log2 = scale * 1.4426950408889634f;
   void* args[] = {&tm_q, &tm_kv, &inner, &utt, &work, &out_b, &ldo, &scale_log2, &prof};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, kinfo_attn_tc().fn, args);
+  cudaError_t e = cudaLaunchKernelExC(&cfg, ki.fn, args);
   if (e != cudaSuccess) {
     *err = std::string("attn_tc_kernel launch: ") + cudaGetErrorString(e);
     return -2;

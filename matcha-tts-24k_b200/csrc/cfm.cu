@@ -36,6 +36,7 @@ std::string g_create_error;
 
 struct GemmW {  // one packed GEMM weight: [n_taps * n_stride, Kp] in the activation type, K-major
   void* w = nullptr;
+  void* w3 = nullptr;  // fp32 mode: bf16 hi / lo split of w, [2 * n_taps * n_stride, Kp] (tensor-core fp32 mode, "fp32_tc")
   float* bias = nullptr;
   int N = 0, K = 0, Kp = 0, n_taps = 1, n_stride = 0;
 };
@@ -113,6 +114,7 @@ struct Plan {
   int xin_ld = 0;
   float *hraw[2], *rres[2], *X[2];
   void *hact[2], *Xn[2], *qkv[2], *ao[2], *ffh[2], *sin_[2], *cat[2];
+  void* split3 = nullptr;  // fp32_tc: bf16 [hi | lo] scratch of the current GEMM's activation operand
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   long long launches_per_solve = 0;
@@ -163,6 +165,8 @@ struct cfm_handle {
   int bf16_mid = 1;                             // tensor-core mode: the conv output between a conv and its GroupNorm-apply and the
                                                 // res_conv output are stored as bf16 (statistics still come from the fp32
                                                 // accumulators), written by row-per-thread epilogues without smem staging; "bf16_mid"
+  int fp32_tc = 0;                              // fp32 handles: GEMMs on the bf16 tensor pipe with bf16 x 3 split operands (hi*hi + lo*hi +
+                                                // hi*lo, fp32 accumulate) instead of the fp32-FMA kernels; "fp32_tc".
   int rowln = 0;                                // Linear + residual + LayerNorm in one kernel (rowln.cuh) for out-proj -> norm3 and FF2 -> next
                                                 // block's norm1: 0 off, 1 for plans above `small_tiles` rows, 2 always; "rowln".
   int rowln_ff2 = 1;                            // also fuse FF2 -> next norm1 (K = 4C); "rowln_ff2".
@@ -363,12 +367,18 @@ int pack_into(cfm_handle* h, GemmW& g, const float* src, long long s_n, long lon
     pack_weight_kernel<float><<<blocks, threads>>>(src, s_n, s_k, s_t, g.n_taps, tap_k, N, g.K,
                                                    static_cast<float*>(g.w) + (long long)row0 * g.Kp, g.Kp, g.n_stride);
   CK(cudaGetLastError());
+  if (!h->bf && g.w3) {  // keep the bf16 hi / lo split of the whole weight current (idempotent; weights are packed once per checkpoint)
+    const long long n = (long long)g.n_taps * g.n_stride * g.Kp;
+    split3_weight_kernel<<<(int)((n + 255) / 256), 256>>>(static_cast<const float*>(g.w), n, static_cast<bf16*>(g.w3));
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 
 int alloc_gemm(cfm_handle* h, GemmW& g, int N, int K, int n_taps) {
   g.N = N, g.K = K, g.Kp = roundup(K, 64), g.n_taps = n_taps, g.n_stride = roundup(N, 64);
   CKR(dev_alloc(h, h->wallocs, &g.w, (size_t)g.n_taps * g.n_stride * g.Kp * h->es));
+  if (!h->bf) CKR(dev_alloc(h, h->wallocs, &g.w3, (size_t)2 * g.n_taps * g.n_stride * g.Kp * sizeof(bf16)));
   return 0;
 }
 
@@ -657,7 +667,32 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   if (h->stopped()) return 0;
   h->launch_counter++;
   CKR(tl_mark(h, s, h->tag, p.M, p.N, p.K * p.n_taps, 2.0 * p.M * p.N * p.K * p.n_taps));
-  const bool tc = h->bf && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  bool tc = h->bf && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  const bool x3 = !h->bf && h->fp32_tc && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM) && h->plan && h->plan->split3 && p.W3 &&
+                  p.n_taps * 3 <= MAX_TAPS && p.K % 64 == 0 && p.lda[0] % 4 == 0 && p.lda[0] <= 4 * h->C() && !p.A[1];
+  if (x3) {
+    // fp32 mode on the tensor pipe: the activation operand is split into bf16 [hi | lo] (one pass), every tap becomes three
+    // (activation range, weight range) pairs hi*hi + lo*hi + hi*lo accumulated in fp32 by the bf16 kernels; fp32 results.
+    const long long lda = p.lda[0], rows = p.a_rows[0];
+    const long long quads = rows * (lda / 4);
+    h->launch_counter++;
+    CKR(launch_ex(h, split3_rows_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, s, 1, static_cast<const float*>(p.A[0]), lda, rows,
+                  static_cast<bf16*>(h->plan->split3)));
+    const int nt = p.n_taps;
+    GemmTap t3[MAX_TAPS];
+    for (int t = 0; t < nt; ++t) {
+      const GemmTap o = p.taps[t];
+      t3[3 * t] = o;
+      t3[3 * t + 1] = o, t3[3 * t + 1].a_col = o.a_col + (int)lda;
+      t3[3 * t + 2] = o, t3[3 * t + 2].w_row = o.w_row + p.w_rows;
+    }
+    for (int t = 0; t < 3 * nt; ++t) p.taps[t] = t3[t];
+    p.n_taps = 3 * nt;
+    p.A[0] = h->plan->split3, p.lda[0] = 2 * lda;
+    p.W = p.W3, p.w_rows = 2 * p.w_rows;
+    p.act_f32 = 1;
+    tc = true;
+  }
   if (!tc) {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
     if (h->bf)
@@ -682,8 +717,8 @@ int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   // activation copy is wanted (L2 performs x += acc + bias through cp.reduce.async.bulk).
   const bool bf_mode = p.mode == EPI_STORE || p.mode == EPI_SNAKE || p.mode == EPI_MASK;
   const bool red_mode = p.mode == EPI_RESID && p.out_act == nullptr && p.resid != nullptr && p.resid == p.out_f32 && p.ld_resid == p.ld_f32;
-  p.tma_epi = (((h->tma_epi >> p.mode) & 1) && (bf_mode || red_mode) && p.N % 8 == 0 && bn % 32 == 0) ? 1 : 0;
-  p.direct_epi = (((h->direct_epi >> p.mode) & 1) && bf_mode && !p.tma_epi && p.N % 32 == 0 && p.ld_act % 16 == 0 &&
+  p.tma_epi = (((h->tma_epi >> p.mode) & 1) && ((bf_mode && !p.act_f32) || red_mode) && p.N % 8 == 0 && bn % 32 == 0) ? 1 : 0;
+  p.direct_epi = (((h->direct_epi >> p.mode) & 1) && bf_mode && !p.act_f32 && !p.tma_epi && p.N % 32 == 0 && p.ld_act % 16 == 0 &&
                   (reinterpret_cast<uintptr_t>(p.out_act) & 31) == 0) ? 1 : 0;
   CUtensorMap tmO = tmA[0];
   if (p.tma_epi) {
@@ -713,6 +748,7 @@ GemmParams gemm_base(int M, const void* A, long long lda, int a_rows, const Gemm
   }
   p.A[0] = A, p.lda[0] = lda, p.a_rows[0] = a_rows;
   p.W = w.w, p.ldw = w.Kp, p.w_rows = w.n_taps * w.n_stride;
+  p.W3 = w.w3;
   p.bias = w.bias;
   p.row_mul = 1, p.row_add = 0;
   return p;
@@ -874,6 +910,15 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
     CKR(tl_mark(h, s, "attention", R.M, I, 0, fl));
   }
   const float scale = 1.0f / sqrtf((float)D);
+  if (!h->bf && h->fp32_tc && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN) && h->plan && h->plan->split3 && 6LL * I <= 8LL * h->C()) {
+    // fp32 mode on the tensor pipe: bf16 [hi | lo] copy of the QKV rows, then the split-operand attention kernel (fp32 output)
+    const long long quads = (long long)R.M_all * (3 * I / 4);
+    h->launch_counter++;
+    CKR(launch_ex(h, split3_rows_kernel, dim3((unsigned)((quads + 255) / 256)), dim3(256), 0, s, 1, static_cast<const float*>(R.qkv_all), 3LL * I,
+                  (long long)R.M_all, static_cast<bf16*>(h->plan->split3)));
+    return launch_attn_tc(h->encode, h->plan->split3, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, nullptr,
+                          h->pdl_now != 0, true);
+  }
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
   if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl_now != 0);
   {
@@ -1365,7 +1410,8 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
     return fail(h, CFM_ERR_INVALID, "invalid estimator configuration");
   if ((cfg->n_heads * cfg->head_dim) % 64 != 0) return fail(h, CFM_ERR_INVALID, "heads*head_dim must be a multiple of 64");
   if (cfg->out_channels % 4 != 0) return fail(h, CFM_ERR_INVALID, "out_channels must be a multiple of 4");
-  if (cfg->precision != CFM_PREC_BF16 && cfg->precision != CFM_PREC_FP32) return fail(h, CFM_ERR_INVALID, "unknown precision");
+  if (cfg->precision != CFM_PREC_BF16 && cfg->precision != CFM_PREC_FP32 && cfg->precision != CFM_PREC_FP32_TC)
+    return fail(h, CFM_ERR_INVALID, "unknown precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(h, CFM_ERR_CUDA, "no CUDA device: libcfm_b200 has no CPU path");
@@ -1378,6 +1424,7 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   h = new cfm_handle();
   h->cfg = *cfg;
   h->bf = cfg->precision == CFM_PREC_BF16;
+  h->fp32_tc = cfg->precision == CFM_PREC_FP32_TC ? 1 : 0;
   h->es = h->bf ? 2 : 4;
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("CFM_B200_PDL")) h->pdl = atoi(e) < 0 ? -1 : atoi(e) != 0;
@@ -1573,6 +1620,7 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
   wfirst1[batch] = pl->n_work1, wfirst2[batch] = pl->n_work2;
   {  // ---- lanes: contiguous utterance groups of equal estimated cost  L (274 C^2 + 1800 C) + 24 C L^2  
     int n_lanes = std::max(1, std::min(h->lanes_req, batch));
+    if (!h->bf && h->fp32_tc) n_lanes = 1;  // the split-operand scratch buffer is shared by every launch of the chain
     n_lanes = std::max(1, std::min(n_lanes, pl->M1 / std::max(1, h->lane_min_rows)));
     if (h->stop_after >= 0) n_lanes = 1;  // the debug launch counter is meaningful for a single chain only
     const double Cd = h->C();
@@ -1668,6 +1716,9 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
     CKR(plan_alloc(h, pl, &pl->sin_[r], M * C * es));
     CKR(plan_alloc(h, pl, &pl->cat[r], M * 2 * C * es));
   }
+  pl->split3 = nullptr;
+  if (!h->bf && h->fp32_tc)  // [hi | lo] bf16 copy of the widest GEMM operand (ffh, [M1, 4C]): tensor-core fp32 mode
+    CKR(plan_alloc(h, pl, &pl->split3, (size_t)pl->M1 * 8 * C * sizeof(bf16)));
   CKR(leave_stream(h, ps));  // tables and the cleared workspace are ready before any later call touches them
 
   // ---- the whole ODE loop as one CUDA graph: captured here, or lazily before the plan's (graph_after + 1)-th decode.
@@ -1979,6 +2030,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
   else if (strcmp(key, "rowln") == 0 && value >= 0 && value <= 2) h->rowln = value;
+  else if (strcmp(key, "fp32_tc") == 0) h->fp32_tc = value != 0;
   else if (strcmp(key, "rowln_ff2") == 0) h->rowln_ff2 = value != 0;
   else if (strcmp(key, "bf16_mid") == 0) h->bf16_mid = value != 0;
   else if (strcmp(key, "bn_full") == 0) h->bn_full = value;

@@ -54,6 +54,7 @@ struct GemmParams {
   const void* W;  // [w_rows, ldw] K-major
   long long ldw;
   int w_rows;
+  const void* W3;  // fp32 mode only: bf16 [2 w_rows, ldw], rows [0, w_rows) = hi, [w_rows, 2 w_rows) = lo parts of W (bf16 x 3 split)
   int mode;
   const float* bias;
   int row_mul, row_add;  // logical row (for row_info) = m * row_mul + row_add
@@ -77,6 +78,7 @@ struct GemmParams {
   int cluster;  // CTAs per cluster sharing one weight tile via TMA multicast (1, 2 or 4)
   int pair;     // 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 per pair)
   int direct_epi;  // 1: epilogue_tile_direct (bf16 modes: rows stored straight from registers with 256-bit stores, no smem)
+  int act_f32;  // 1: out_act is fp32 (the fp32 precision mode on the tensor pipe, bf16x3 split operands): generic epilogue only, precise sine
   int tma_epi;  // 1: epilogue_tile_tma (row-per-thread math, swizzled smem staging, TMA store / reduce-add); see launch_gemm
   unsigned long long* prof;  // debug: CTA 0 writes per-role cycle counters (see gemm_tc_kernel); nullptr = off
 };
@@ -95,6 +97,15 @@ template <> struct ActIO<bf16> {
   // bf16 rounding of the result for the arguments SnakeBeta sees (|h * e^alpha| up to a few hundred).
   static __device__ __forceinline__ float fsin(float x) { return __sinf(x); }
 };
+
+// sine for the tensor-core fp32 mode: two-constant Cody-Waite reduction to [-pi, pi], then MUFU.SIN (absolute error ~5e-7 for the
+// arguments SnakeBeta sees; sinf's slow path for large arguments cost 100 us per FF1 launch)
+__device__ __forceinline__ float sin_reduced(float x) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555e-07f, r);
+  return __sinf(r);
+}
 
 template <typename T, int NV>
 __device__ __forceinline__ void store_act(T* dst, const float (&v)[NV], bool /*unused*/ = true) {
@@ -405,6 +416,10 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
   const bool split = rb > 0;
   int cur_utt = -1;
   bf16* oact = reinterpret_cast<bf16*>(p.out_act);
+  auto store_act4 = [&](int m, float a0, float a1, float a2, float a3) {  // 4 columns of row m in the activation type
+    if (p.act_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + (long long)m * p.ld_act + n) = make_float4(a0, a1, a2, a3);
+    else *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(a0, a1, a2, a3);
+  };
   // All global loads of the block are issued before any store: the residual stream is updated in place, so the compiler
   // must otherwise order every load behind the previous row's store and exposes one memory round trip per row.
   float4 rv[8];
@@ -429,7 +444,7 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
     float x0 = a.x + b4.x, x1 = a.y + b4.y, x2 = a.z + b4.z, x3 = a.w + b4.w;
     const bool valid = (valid_mask >> r) & 1u;
     if constexpr (MODE == EPI_STORE) {
-      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+      store_act4(m, x0, x1, x2, x3);
     } else if constexpr (MODE == EPI_STATS) {
       *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
       if (do_stats && (stats_uniform || split)) {
@@ -460,16 +475,17 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = make_float4(x0, x1, x2, x3);
       if (oact) {
         if (!valid) x0 = x1 = x2 = x3 = 0.f;
-        *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+        store_act4(m, x0, x1, x2, x3);
       }
     } else if constexpr (MODE == EPI_SNAKE) {
-      float s0 = ActIO<bf16>::fsin(x0 * ea4.x), s1 = ActIO<bf16>::fsin(x1 * ea4.y);
-      float s2 = ActIO<bf16>::fsin(x2 * ea4.z), s3 = ActIO<bf16>::fsin(x3 * ea4.w);
+      float s0, s1, s2, s3;
+      if (p.act_f32) s0 = sin_reduced(x0 * ea4.x), s1 = sin_reduced(x1 * ea4.y), s2 = sin_reduced(x2 * ea4.z), s3 = sin_reduced(x3 * ea4.w);
+      else s0 = ActIO<bf16>::fsin(x0 * ea4.x), s1 = ActIO<bf16>::fsin(x1 * ea4.y), s2 = ActIO<bf16>::fsin(x2 * ea4.z), s3 = ActIO<bf16>::fsin(x3 * ea4.w);
       x0 = fmaf(s0 * s0, ib4.x, x0), x1 = fmaf(s1 * s1, ib4.y, x1), x2 = fmaf(s2 * s2, ib4.z, x2), x3 = fmaf(s3 * s3, ib4.w, x3);
-      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+      store_act4(m, x0, x1, x2, x3);
     } else if constexpr (MODE == EPI_MASK) {
       if (!valid) x0 = x1 = x2 = x3 = 0.f;
-      *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(x0, x1, x2, x3);
+      store_act4(m, x0, x1, x2, x3);
     } else {  // EPI_ODE
       if (!valid) x0 = x1 = x2 = x3 = 0.f;
       float4 y = rv[it];
@@ -485,7 +501,7 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, uint32_t stg, int
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_f32 + n) = y;
       if (oact) {
         if (!valid) y = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<uint2*>(oact + (long long)m * p.ld_act + n) = pack4_bf16(y.x, y.y, y.z, y.w);
+        store_act4(m, y.x, y.y, y.z, y.w);
       }
     }
   }
@@ -632,7 +648,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     }
   }
   constexpr bool WIDE = (MODE == EPI_STORE || MODE == EPI_SNAKE || MODE == EPI_MASK);
-  const bool wide = WIDE && (p.N % 8 == 0);
+  const bool wide = WIDE && (p.N % 8 == 0) && !p.act_f32;
   uint32_t r0[16], r1[16];
   if (half < BN / 32) {
     ptx::tmem_ld16(taddr + half * 32, r0);
@@ -1502,6 +1518,6 @@ CFM_FOR_EACH_TC(CFM_X_TC)
 CFM_FOR_EACH_TC2(CFM_X_TC2)
 #undef CFM_X_TC
 #undef CFM_X_TC2
-KernelInfo kinfo_attn_tc();
+KernelInfo kinfo_attn_tc(int x3);
 
 }  // namespace cfm

@@ -66,6 +66,40 @@ __device__ __forceinline__ void ld8(const bf16* p, float4& lo, float4& hi) {
   lo = make_float4(a.x, a.y, b.x, b.y), hi = make_float4(c.x, c.y, d.x, d.y);
 }
 
+// ---------------------------------------------------------------------------------- bf16 x 3 split (fp32 mode on the tensor pipe)
+// a = hi + lo + r with hi = bf16(a), lo = bf16(a - hi), |r| <= 2^-18 |a|.  A product a * w is taken as hi*hi + lo*hi + hi*lo on
+// the bf16 tensor pipe with fp32 accumulation (the dropped terms are ~2^-17 relative): the GEMM sees [hi | lo] as two K ranges of
+// one wider operand and three (activation range, weight range) pairs per tap.
+// src: [rows, ld] fp32 -> dst: [rows, 2 ld] bf16, hi in columns [0, ld), lo in [ld, 2 ld).  ld % 4 == 0.
+static __global__ void split3_rows_kernel(const float* __restrict__ src, long long ld, long long rows, bf16* __restrict__ dst) {
+  ptx::pdl_wait();
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+  const long long per_row = ld >> 2;
+  if (q >= rows * per_row) return;
+  const long long r = q / per_row, c = (q - r * per_row) << 2;
+  const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+  ptx::pdl_launch_dependents();
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float2bfloat16_rn(a[i]);
+    lo[i] = __float2bfloat16_rn(a[i] - __bfloat162float(hi[i]));
+  }
+  bf16* d = dst + r * 2 * ld + c;
+  *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(d + ld) = *reinterpret_cast<const uint2*>(lo);
+}
+// Weights: [rows, ld] fp32 -> [2 rows, ld] bf16, hi in rows [0, rows), lo in rows [rows, 2 rows).
+static __global__ void split3_weight_kernel(const float* __restrict__ src, long long n, bf16* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = src[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+  dst[i] = hi;
+  dst[n + i] = __float2bfloat16_rn(a - __bfloat162float(hi));
+}
+
 // ---------------------------------------------------------------------------------- pack / unpack
 // (B, F, T) fp32 channels-first  ->  rows [start_b + t], columns [col0, col0 + F) of a token-major buffer.
 // Rows t >= L of the utterance's segment are written as zero.  Optionally also writes the fp32 state.

@@ -18,7 +18,7 @@ def main():
     reps = int(os.environ.get("AB_REPS", "5"))
     only = [t for t in os.environ.get("AB_TAGS", "").split(",") if t]
     cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
-    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision="bf16").eval().cuda()
+    m = P.CFM(200, 100, cp, P.synthetic.PROD, precision=os.environ.get("AB_PRECISION", "bf16")).eval().cuda()
     P.synthetic.fill_named_seed(m.estimator, 1234)
     m.refresh(torch.device("cuda", 0))
     lengths = P.synthetic.config_lengths(wl)

@@ -19,6 +19,8 @@ def rel(a, b):
 
 def main():
     settings = [""] + sys.argv[1:]
+    prec = os.environ.get("OC_PRECISION", "bf16")
+    tol = 1.2e-2 if prec == "bf16" else 1e-3
     cp = types.SimpleNamespace(solver="euler", sigma_min=1e-4, use_mu_prior=True)
     cases = (("prod", P.synthetic.PROD, [300, 171, 64, 129, 1]), ("prod_long", P.synthetic.PROD, [938, 517]),
              ("default", P.synthetic.DEFAULT, [257, 130]))
@@ -31,7 +33,7 @@ def main():
         with torch.inference_mode():
             ref_e = ora.estimator(z, mask, mu, torch.tensor(0.4))
             ref_s = ora.solve(z, ts, mu, mask)
-        m = P.CFM(200, 100, cp, dec, precision="bf16").eval()
+        m = P.CFM(200, 100, cp, dec, precision=prec).eval()
         m.estimator.load_state_dict(ora.estimator.state_dict())
         m = m.cuda()
         m.refresh(torch.device("cuda", 0))
@@ -46,7 +48,7 @@ def main():
             if base is None:
                 base = (e, s)
             fin = bool(torch.isfinite(e).all() and torch.isfinite(s).all())
-            good = fin and rel(e, ref_e) < 1.2e-2 and rel(s, ref_s) < 1.2e-2
+            good = fin and rel(e, ref_e) < tol and rel(s, ref_s) < tol
             ok = ok and good
             print(f"[{name}] [{setting or 'defaults'}] estimator vs oracle {rel(e, ref_e):.3e} vs default {rel(e, base[0]):.3e} | "
                   f"solve vs oracle {rel(s, ref_s):.3e} vs default {rel(s, base[1]):.3e} finite={fin} {'ok' if good else 'FAIL'}", flush=True)
