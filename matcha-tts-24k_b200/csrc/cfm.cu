@@ -662,14 +662,19 @@ int set_gemm_attrs(cfm_handle* h) {
   return 0;
 }
 
+// fp32 handle with "fp32_tc": can this GEMM run on the bf16 tensor pipe with split operands (launch_gemm)?
+bool x3_ok(const cfm_handle* h, const GemmParams& p) {
+  return !h->bf && h->fp32_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM) && h->plan && h->plan->split3 && p.W3 && p.n_taps * 3 <= MAX_TAPS &&
+         p.K % 64 == 0 && p.lda[0] % 4 == 0 && p.lda[0] <= 4 * h->C() && !p.A[1];
+}
+
 // A sources: p.A / p.lda / p.a_rows already describe element-addressed matrices.
 int launch_gemm(cfm_handle* h, GemmParams& p, bool allow_tc, cudaStream_t s) {
   if (h->stopped()) return 0;
   h->launch_counter++;
   CKR(tl_mark(h, s, h->tag, p.M, p.N, p.K * p.n_taps, 2.0 * p.M * p.N * p.K * p.n_taps));
   bool tc = h->bf && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
-  const bool x3 = !h->bf && h->fp32_tc && allow_tc && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM) && h->plan && h->plan->split3 && p.W3 &&
-                  p.n_taps * 3 <= MAX_TAPS && p.K % 64 == 0 && p.lda[0] % 4 == 0 && p.lda[0] <= 4 * h->C() && !p.A[1];
+  const bool x3 = allow_tc && x3_ok(h, p);
   if (x3) {
     // fp32 mode on the tensor pipe: the activation operand is split into bf16 [hi | lo] (one pass), every tap becomes three
     // (activation range, weight range) pairs hi*hi + lo*hi + hi*lo accumulated in fp32 by the bf16 kernels; fp32 results.
@@ -850,7 +855,7 @@ int run_conv_stats(cfm_handle* h, Plan* pl, const Res& R, const void* A, long lo
   p.row_info = R.info;
   p.stats = pl->stats + (long long)site * pl->B * 16;
   p.group_ch = h->C() / 8;
-  const bool tc = h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM);
+  const bool tc = (h->bf && !(h->cfg.flags & CFM_FLAG_SIMT_GEMM)) || x3_ok(h, p);  // x3: sums from the fp32 accumulators, like bf16
   p.fused_stats = (tc && !(h->cfg.flags & CFM_FLAG_UNFUSED_STATS)) ? 1 : 0;
   CKR(launch_gemm(h, p, true, s));
   if (!p.fused_stats && !h->stopped()) {
