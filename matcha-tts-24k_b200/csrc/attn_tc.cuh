@@ -164,6 +164,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const uint32_t v_addr = ptx::smem_u32(smem + Cfg::OFF_V), p_addr = ptx::smem_u32(smem + Cfg::OFF_P);
       unsigned long long wq = 0, wk = 0, wp = 0, wv = 0;
       const long long t_start = clock64();
+      const unsigned long long t_start_ns = prof != nullptr ? ptx::globaltimer_ns() : 0ull;
       auto issue_s = [&](int j) {
         const int b = j & 1;
         mbar_wait_prof(bar_k + b, (j >> 1) & 1, do_prof, wk);
@@ -200,6 +201,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       if (do_prof && lane == 0) {
         prof[0] = (unsigned long long)(clock64() - t_start), prof[1] = wq, prof[2] = wk, prof[3] = wp, prof[4] = wv;
         prof[5] = (unsigned long long)n_tiles;
+      }
+      if (prof != nullptr && lane == 0 && gridDim.x <= 4096) {  // every CTA: MMA-warp lifetime [cycles], start / end [ns], SM id
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* q = prof + 32 + 4ull * blockIdx.x;
+        q[0] = (unsigned long long)(clock64() - t_start), q[1] = t_start_ns, q[2] = ptx::globaltimer_ns(), q[3] = smid;
       }
     }
   } else {

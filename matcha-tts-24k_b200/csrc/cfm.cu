@@ -1652,6 +1652,12 @@ int cfm_plan(cfm_handle* h, const int32_t* lengths, int32_t batch, int32_t t_pad
       pl->lanes.push_back(ln);
       b0 = b1;
     }
+    // Attention CTAs cost ~ the utterance's key tiles: longest first within a lane, so that the last, partly filled wave of the grid
+    // holds the shortest items (ragged batches: cfg3)
+    for (const LaneDef& ln : pl->lanes) {
+      std::stable_sort(w1.begin() + ln.w0[0], w1.begin() + ln.w0[0] + ln.nw[0], [&](const int4& a, const int4& b) { return u1[a.x].len > u1[b.x].len; });
+      std::stable_sort(w2.begin() + ln.w0[1], w2.begin() + ln.w0[1] + ln.nw[1], [&](const int4& a, const int4& b) { return u2[a.x].len > u2[b.x].len; });
+    }
     while ((int)h->lane_streams.size() + 1 < n_lanes) {
       cudaStream_t st;
       cudaEvent_t ev;

@@ -259,7 +259,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool prof = prof0 && warp == 4;
     unsigned long long w_h = 0, w_y = 0, t_tail = 0, t_ld = 0, t_math = 0, t_st = 0;
     const long long t_start = clock64();
-    GemmParams gp;  // the tile epilogue reuses the GEMM epilogues of gemm.cuh (EPI_RESID)
+    GemmParams gp = {};  // the tile epilogue reuses the GEMM epilogues of gemm.cuh (EPI_RESID); every other field zero
     gp.M = p.M, gp.N = C, gp.mode = EPI_RESID, gp.bias = p.b2, gp.row_mul = 1, gp.row_add = 0, gp.row_info = p.row_info;
     gp.resid = p.X, gp.ld_resid = p.ldx, gp.out_f32 = p.X, gp.ld_f32 = p.ldx, gp.out_act = p.copy, gp.ld_act = p.ld_copy;
     gp.fused_stats = 0, gp.stats = nullptr;

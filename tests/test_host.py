@@ -139,3 +139,15 @@ def test_sharding_is_balanced_and_complete():
 def test_flop_model_matches_survey():
     assert abs(P.synthetic.algorithmic_flops([938] * 32, 384, 10) / 14.93e12 - 1) < 2e-3
     assert abs(P.synthetic.algorithmic_flops([150], 384, 10) / 63.7e9 - 1) < 5e-3
+
+
+def test_precision_names_match_the_header():
+    """cfm_precision in include/cfm_b200.h <-> the names the host module accepts (bf16 / fp32 / fp32_tc)."""
+    import re
+    from matcha_tts_24k_b200 import _native as N
+    src = open(os.path.join(ROOT, "include", "cfm_b200.h")).read()
+    enum = re.search(r"typedef enum \{([^}]*)\} cfm_precision;", src).group(1)
+    vals = {k.strip().lower().replace("cfm_prec_", ""): int(v) for k, v in (item.split("=") for item in enum.split(","))}
+    assert vals == N.PREC
+    with pytest.raises(ValueError):
+        P.CFM(200, 100, cfm_params("euler"), P.synthetic.PROD, precision="fp16")

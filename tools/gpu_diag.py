@@ -550,7 +550,7 @@ def c_attnprof():
     lengths = [938] * 32
     mu, mask, z, _ = P.synthetic.make_inputs(lengths, seed=1, device="cuda")
     m.estimator(z, mask, mu, torch.tensor(0.3))
-    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(32 + 4 * 4096, dtype=torch.int64, device="cuda")
     m._lib.cfm_debug_attn_profile(m._handle, prof.data_ptr())
     m._lib.cfm_debug_stop_after(m._handle, 12)  # memset, conv1, res, gn, conv2, gn, LN, QKV, attention
     m.estimator(z, mask, mu, torch.tensor(0.3))
@@ -558,6 +558,22 @@ def c_attnprof():
     p = prof.tolist()
     print(f"[attnprof] tiles={p[5]} | mma thread: total={p[0]} wait_q={p[1]} wait_k={p[2]} wait_p={p[3]} wait_v={p[4]} | "
           f"softmax warp: total={p[8]} wait_s={p[9]} wait_rowmax_barrier={p[10]} wait_pv={p[11]}")
+    # per-CTA lifetimes: the grid is 32 utterances x 6 heads x 8 query tiles = 1536 CTAs, two resident per SM
+    n = 1536
+    cyc = [p[32 + 4 * i] for i in range(n)]
+    t0 = [p[32 + 4 * i + 1] for i in range(n)]
+    t1 = [p[32 + 4 * i + 2] for i in range(n)]
+    base = min(t0)
+    import statistics as st
+    print(f"[attnprof] per-CTA MMA-warp lifetime [cycles]: min {min(cyc)} median {st.median(cyc)} mean {st.mean(cyc):.0f} max {max(cyc)}; "
+          f"kernel span {(max(t1) - base) / 1e3:.1f} us")
+    order = sorted(range(n), key=lambda i: t0[i])
+    for lo in range(0, n, 296):
+        grp = order[lo:lo + 296]
+        print(f"   CTAs started {lo}-{lo + len(grp) - 1}: start {(min(t0[i] for i in grp) - base) / 1e3:6.1f}-{(max(t0[i] for i in grp) - base) / 1e3:6.1f} us, "
+              f"lifetime {st.mean((t1[i] - t0[i]) for i in grp) / 1e3:5.1f} us mean, {st.mean(cyc[i] for i in grp):.0f} cycles mean")
+    last = sorted(t1)
+    print(f"   50 % of the CTAs done at {(last[n // 2] - base) / 1e3:.1f} us, 90 % at {(last[int(n * 0.9)] - base) / 1e3:.1f} us, all at {(last[-1] - base) / 1e3:.1f} us")
 
 
 def c_plantime():
