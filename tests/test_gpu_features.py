@@ -188,6 +188,36 @@ def test_fused_linear_layernorm_kernel_matches_unfused_schedule(dec, lengths):
     m.close()
 
 
+@pytest.mark.parametrize("dec,lengths,in_ch", [(syn.DEFAULT, [257, 130, 3], 200), (syn.PROD, [150, 97], 216), (SMALL, [150, 97, 64], 200)])
+def test_fp32_on_the_tensor_pipe_matches_oracle_and_fp32_reference(dec, lengths, in_ch):
+    """precision "fp32_tc" (fp32 storage, bf16 x 3 split operands through the bf16 GEMM kernels and the split-operand attention
+    kernel): <= 1e-3 of the oracle (north_star's fp32 tolerance; measured ~1e-5) and of the library's fp32-FMA mode, for the default
+    C = 320 estimator, speaker channels (S = 16) and a 128-wide estimator; solve, per-utterance-t estimator call, option toggling."""
+    ora, m = pair(dec, precision="fp32_tc", in_channels=in_ch)
+    S = in_ch - 200
+    mu, mask, z, _ = syn.make_inputs(lengths, seed=63)
+    spks = torch.randn(len(lengths), S, generator=torch.Generator().manual_seed(2)) if S else None
+    ts = torch.linspace(0, 1, 4)
+    ref = ora.solve(z, ts, mu, mask, spks) if S else ora.solve(z, ts, mu, mask)
+    kw = {"spks": spks.cuda()} if S else {}
+    out = m.solve(z.cuda(), ts, mu.cuda(), mask.cuda(), **kw).cpu()
+    err = rel_l2(out, ref)
+    print(f"fp32_tc solve: rel_l2 vs oracle {err:.3e} max_abs {float((out - ref).abs().max()):.3e}")
+    assert torch.isfinite(out).all() and err <= 1e-3
+    for b, L in enumerate(lengths):
+        assert torch.equal(out[b, :, L:], z[b, :, L:])
+    if not S:
+        t = torch.rand(len(lengths), generator=torch.Generator().manual_seed(4))
+        v = m.estimator(z.cuda(), mask.cuda(), mu.cuda(), t).cpu()
+        with torch.inference_mode():
+            v_ref = ora.estimator(z, mask, mu, t)
+        assert rel_l2(v, v_ref) <= 1e-3
+        m.set_option("fp32_tc", 0)  # the same handle as the fp32-FMA reference mode
+        exact = m.solve(z.cuda(), ts, mu.cuda(), mask.cuda()).cpu()
+        assert rel_l2(exact, ref) <= 2e-5 and rel_l2(out, exact) <= 1e-3
+    m.close()
+
+
 def _sharded_case(devices):
     lengths = [120, 64, 97, 33, 150, 88, 140]
     ora, single = pair(SMALL, precision="fp32")
