@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libcfm_b200.so")
-HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", "attn.cuh", "attn_tc.cuh", "ff_fused.cuh", "rowln.cuh", os.path.join("..", "..", "include", "cfm_b200.h")]
+HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", "attn.cuh", "attn_tc.cuh", "attn_persist.cuh", "ff_fused.cuh", "rowln.cuh", os.path.join("..", "..", "include", "cfm_b200.h")]
 TC = [(64, 8), (128, 8), (160, 8), (192, 8), (256, 8), (256, 12)]  # gemm_tc_kernel<BN, epilogue warps>  (gemm.cuh CFM_FOR_EACH_TC)
 TC2 = [128, 160, 192, 256]                                          # gemm_tc2_kernel<BN>                  (CFM_FOR_EACH_TC2)
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

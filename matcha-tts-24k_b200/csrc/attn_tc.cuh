@@ -361,8 +361,8 @@ KernelInfo kinfo_attn_tc(int x3) {
 #else
 
 inline int attn_tc_set_attr(std::string* err) {
-  for (int x3 = 0; x3 < 2; ++x3) {
-    const KernelInfo k = kinfo_attn_tc(x3);
+  for (int x3 = 0; x3 < 3; ++x3) {
+    const KernelInfo k = x3 == 2 ? kinfo_attn_persist() : kinfo_attn_tc(x3);
     cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem);
     if (e != cudaSuccess) {
       *err = std::string("cudaFuncSetAttribute(attn_tc_kernel): ") + cudaGetErrorString(e);

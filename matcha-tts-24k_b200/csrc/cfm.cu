@@ -19,6 +19,7 @@
 #include "../../include/cfm_b200.h"
 #include "attn.cuh"
 #include "attn_tc.cuh"
+#include "attn_persist.cuh"
 #include "ff_fused.cuh"
 #include "rowln.cuh"
 #include "gemm.cuh"
@@ -167,6 +168,7 @@ struct cfm_handle {
                                                 // accumulators), written by row-per-thread epilogues without smem staging; "bf16_mid"
   int fp32_tc = 0;                              // fp32 handles: GEMMs on the bf16 tensor pipe with bf16 x 3 split operands (hi*hi + lo*hi +
                                                 // hi*lo, fp32 accumulate) instead of the fp32-FMA kernels; "fp32_tc".
+  int attn_persist = 1;                         // persistent attention kernel (attn_persist.cuh): items streamed through one pipeline; "attn_persist".
   int rowln = 0;                                // Linear + residual + LayerNorm in one kernel (rowln.cuh) for out-proj -> norm3 and FF2 -> next
                                                 // block's norm1: 0 off, 1 for plans above `small_tiles` rows, 2 always; "rowln".
   int rowln_ff2 = 1;                            // also fuse FF2 -> next norm1 (K = 4C); "rowln_ff2".
@@ -925,6 +927,9 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
                           h->pdl_now != 0, true);
   }
   const bool tc = h->bf && D == 64 && !(h->cfg.flags & CFM_FLAG_SIMT_ATTN);
+  if (tc && h->attn_persist && !h->attn_prof)
+    return launch_attn_persist(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, 2 * h->sm_count, s, &h->err,
+                               h->pdl_now != 0);
   if (tc) return launch_attn_tc(h->encode, R.qkv_all, 3LL * I, I, R.M_all, R.utt, R.work, R.n_work, R.ao_all, I, scale, s, &h->err, h->attn_prof, h->pdl_now != 0);
   {
     const KernelInfo k = h->bf ? (D == 64 ? kinfo_attn_simt_bf16_64() : kinfo_attn_simt_bf16_32())
@@ -2041,6 +2046,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
   else if (strcmp(key, "rowln") == 0 && value >= 0 && value <= 2) h->rowln = value;
+  else if (strcmp(key, "attn_persist") == 0) h->attn_persist = value != 0;
   else if (strcmp(key, "fp32_tc") == 0) h->fp32_tc = value != 0;
   else if (strcmp(key, "rowln_ff2") == 0) h->rowln_ff2 = value != 0;
   else if (strcmp(key, "bf16_mid") == 0) h->bf16_mid = value != 0;

@@ -1519,5 +1519,6 @@ CFM_FOR_EACH_TC2(CFM_X_TC2)
 #undef CFM_X_TC
 #undef CFM_X_TC2
 KernelInfo kinfo_attn_tc(int x3);
+KernelInfo kinfo_attn_persist();
 
 }  // namespace cfm

@@ -59,7 +59,8 @@ def main():
             print(f"    {tag:24s} {a[0] / 1e3:7.3f} ms  {a[2] // 2:4d} launches  {a[0] / max(1, a[2] // 2):7.1f} us/launch  {tf:7.1f} TFLOP/s", flush=True)
         for k in opts:
             base.setdefault(k, {"bn_full": 0, "bn_half": 0, "pair_min_k": 1024, "pair_mode": 1, "tma_epi": 4, "direct_epi": 17, "snake_warps": 12,
-                                "pair_n256": 0, "small_tiles": 1024, "l2_persist_mb": 32, "pdl": -1, "cluster": 1}.get(k, 0))
+                                "pair_n256": 0, "small_tiles": 1024, "l2_persist_mb": 32, "pdl": -1, "cluster": 1, "attn_persist": 1, "bf16_mid": 1,
+                                "rowln_ff2": 1}.get(k, 0))
 
 
 if __name__ == "__main__":

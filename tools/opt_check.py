@@ -53,7 +53,7 @@ def main():
             print(f"[{name}] [{setting or 'defaults'}] estimator vs oracle {rel(e, ref_e):.3e} vs default {rel(e, base[0]):.3e} | "
                   f"solve vs oracle {rel(s, ref_s):.3e} vs default {rel(s, base[1]):.3e} finite={fin} {'ok' if good else 'FAIL'}", flush=True)
             for k in opts:  # back to the defaults known to ab_timeline
-                m.set_option(k, {"small_tiles": 1024}.get(k, 0))
+                m.set_option(k, {"small_tiles": 1024, "attn_persist": 1, "bf16_mid": 1, "rowln_ff2": 1}.get(k, 0))
         m.close()
     print("ALL OK" if ok else "SOME FAILED")
 
