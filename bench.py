@@ -14,6 +14,7 @@ A "step" is one full decode (pack -> CUDA graph of the 10-step Euler loop -> unp
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -353,17 +354,36 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    step_ms, host_ms = [], []
+
+    def timed(fn, steps, lead_in=0):
+        """K steps queued back to back between two events.  lead_in: untimed steps queued right before the first event without a
+        synchronisation in between, their results held at the same time.  The loop below keeps the previous result alive while the
+        next decode allocates its output, so the SECOND queued decode needs a second output block from torch's caching allocator;
+        when the cache has none that is a cudaMalloc (+ a release of cached blocks, which waits for the device) inside the call -
+        1-140 ms of host time (`run.step_enqueue_ms`) during which the queue ran dry and the second step looked 2-5x longer.  The
+        lead-in puts both blocks into the cache before the first event."""
+        gc.collect()
+        gc.disable()  # no collection pauses between the enqueues of the timed steps
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]  # one per step: spread of the steps inside the region
+        hold = [fn() for _ in range(lead_in)]  # two results alive at once, as in the loop below (`out` + the new one)
+        del hold
         w0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
+        host_ms.clear()
+        for i in range(steps):
+            h0 = time.perf_counter()
             out = fn()
+            host_ms.append((time.perf_counter() - h0) * 1e3)
+            marks[i].record()
         e1.record()
         barrier()
         wall = time.perf_counter() - w0
         ms = e0.elapsed_time(e1)
+        step_ms[:] = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(steps)]
+        gc.enable()
         t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -384,7 +404,8 @@ def main():
             torch.cuda.synchronize(dev)
             n_w += 1
         lo = clk.mark()
-        ms_total, _, out = timed(dev_step, args.steps)
+        ms_total, _, out = timed(dev_step, args.steps, lead_in=2)
+        dev_step_ms, dev_host_ms = list(step_ms), list(host_ms)
         time.sleep(0.12)
         hi = clk.mark()
     clocks = clk.summary(lo, max(hi, lo + 1))
@@ -446,6 +467,7 @@ def main():
         "config": workload_config(desc, args, T),
         "run": {"batch_per_gpu": len(lengths), "frames_per_gpu": sum(lengths), "rows_full": info["rows_full"],
                 "workspace_mib": round(info["workspace_bytes"] / 2**20), "schedule": "whole ODE loop = one CUDA graph",
+                "step_ms": [round(v, 3) for v in dev_step_ms], "step_enqueue_ms": [round(v, 3) for v in dev_host_ms],
                 "parallelism": "utterance-sharded replicas, no collective" if world > 1 else "single GPU"},
         "rtf": (ms_step * 1e-3) / (job_frames * FRAME_SECONDS),
         "e2e": {"value": job_frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,

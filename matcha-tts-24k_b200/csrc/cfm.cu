@@ -1464,6 +1464,7 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   if (r) return bail(r);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }
   if (cudaEventCreateWithFlags(&h->busy_event, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(CFM_ERR_CUDA); }
+  if (const char* e = getenv("CFM_B200_ATTN_PERSIST")) h->attn_persist = atoi(e) != 0;
   if (const char* e = getenv("CFM_B200_PLAN_CACHE")) h->plan_cache = std::max(1, atoi(e));
   if (const char* e = getenv("CFM_B200_L2_PERSIST_MB")) h->l2_persist_mb = std::max(0, atoi(e));
   if (apply_l2_persist(h, h->l2_persist_mb) != 0) return bail(CFM_ERR_CUDA);

@@ -41,8 +41,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Suspend-time hint of try_wait: the waiting thread is parked by the hardware until the phase completes (or this many ns pass)
 // instead of re-polling - a dozen waiting warps per CTA otherwise burn issue slots and power the capped chip does not have.
+// 50 us, not more: with the persistent attention kernel a decode occasionally (a few times per thousand launches) lost a multiple
+// of the former 10 ms hint - a parked waiter that was not woken by its phase completion sleeps the whole hint - so the hint bounds
+// the cost of a missed wake-up; the longest legitimate waits are a kernel's duration, and one re-poll per 50 us is free.
 #ifndef CFM_SUSPEND_HINT_NS
-#define CFM_SUSPEND_HINT_NS 0x989680
+#define CFM_SUSPEND_HINT_NS 0xC350
 #endif
 constexpr uint32_t kSuspendHintNs = CFM_SUSPEND_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
