@@ -128,6 +128,8 @@ int cfm_set_lanes(cfm_handle* h, int32_t lanes, int32_t min_rows);
  *   "attn_persist" 0/1: persistent attention kernel (csrc/attn_persist.cuh: 2 CTAs per SM stream the (utterance, head, query tile)
  *                 items through one software pipeline, Q and O double-buffered, deferred epilogue) instead of one CTA per item
  *                 (default 1: cfg2 attention 106 -> 99 us per full-resolution call, cfg3 -8 %; bitwise identical results)
+ *   "res_side"    -1/0/1: res_conv of every resnet as a side branch of the CUDA graph (its own stream, fork / join events): automatic
+ *                 (plans of <= 2048 packed rows) / off / on
  *   "rowln"       0/1/2: Linear + residual add + LayerNorm as ONE kernel (csrc/rowln.cuh: a CTA owns whole 128 x C row tiles) for
  *                 out-proj -> norm3 and FF2 -> next block's norm1: off / plans above "small_tiles" rows / always; C % 128 == 0 only
  *                 (default 0: measured equal or slower, header of rowln.cuh); "rowln_ff2" 0/1 excludes / includes the FF2 site

@@ -196,6 +196,10 @@ struct cfm_handle {
   std::vector<cudaStream_t> lane_streams;
   std::vector<cudaEvent_t> lane_events;
   cudaEvent_t fork_event = nullptr;
+  cudaStream_t side_stream = nullptr;            // side branch of the schedule (res_conv), "res_side"
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  int res_side = -1;                             // -1: automatic (plans of <= 2048 packed rows, where every launch is latency-bound: B = 1
+                                                 // 6.65 -> 6.55 ms; neutral on cfg2 / cfg3, where the GPU is saturated), 0 off, 1 on
   int C() const { return cfg.channels; }
   int inner() const { return cfg.n_heads * cfg.head_dim; }
 };
@@ -952,6 +956,15 @@ int run_attention(cfm_handle* h, const Res& R, cudaStream_t s) {
 int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const void* A, long long lda, int& site,
                const float* tproj, long long tproj_stride, cudaStream_t s, const NormW* fuse_ln) {
   const int C = h->C();
+  // res_conv only meets the main chain again at the second GroupNorm-apply: as a side branch (its own stream, fork / join events =
+  // graph edges) it can fill the partly idle last round of conv1 / conv2 and run under the bandwidth-bound apply pass
+  const bool side = (h->res_side < 0 ? pl->M1 <= 2048 : h->res_side != 0) && h->side_stream && pl->lanes.size() == 1 && !h->tl_on &&
+                    h->stop_after < 0;
+  cudaStream_t sr = side ? h->side_stream : s;
+  if (side) {
+    CK(cudaEventRecord(h->side_fork, s));
+    CK(cudaStreamWaitEvent(sr, h->side_fork, 0));
+  }
   CKR(run_conv_stats(h, pl, R, A, lda, w.conv1, site, s));
   {  // res_conv (1x1) on the same masked input -> fp32
     GemmParams p = gemm_base(R.M, A, lda, R.M, w.res, nullptr, nullptr);
@@ -959,11 +972,13 @@ int run_resnet(cfm_handle* h, Plan* pl, const Res& R, const ResnetW& w, const vo
     p.out_f32 = R.rres, p.ld_f32 = C;
     if (mid16(h)) p.mode = EPI_STORE, p.out_act = R.rres, p.ld_act = C;  // bf16 result, direct-store epilogue
     h->tag = "res_conv";
-    CKR(launch_gemm(h, p, true, s));
+    CKR(launch_gemm(h, p, true, sr));
   }
+  if (side) CK(cudaEventRecord(h->side_join, sr));
   CKR(run_gn_apply(h, pl, R, w.gn1, site, tproj, nullptr, nullptr, R.hact, C, s, nullptr, tproj_stride));
   site++;
   CKR(run_conv_stats(h, pl, R, R.hact, C, w.conv2, site, s));
+  if (side) CK(cudaStreamWaitEvent(s, h->side_join, 0));
   CKR(run_gn_apply(h, pl, R, w.gn2, site, nullptr, R.rres, R.X, nullptr, 0, s, fuse_ln));
   site++;
   return 0;
@@ -1463,6 +1478,9 @@ int cfm_create(const cfm_config* cfg, cfm_handle** out) {
   r = r ? r : attn_tc_set_attr(&h->err);
   if (r) return bail(r);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(CFM_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->side_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->side_join, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream / event creation failed"; return bail(CFM_ERR_CUDA); }
   if (cudaEventCreateWithFlags(&h->busy_event, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(CFM_ERR_CUDA); }
   if (const char* e = getenv("CFM_B200_ATTN_PERSIST")) h->attn_persist = atoi(e) != 0;
   if (const char* e = getenv("CFM_B200_PLAN_CACHE")) h->plan_cache = std::max(1, atoi(e));
@@ -1484,6 +1502,9 @@ void cfm_destroy(cfm_handle* h) {
   for (cudaStream_t st : h->lane_streams) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->lane_events) cudaEventDestroy(ev);
   if (h->fork_event) cudaEventDestroy(h->fork_event);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->side_fork) cudaEventDestroy(h->side_fork);
+  if (h->side_join) cudaEventDestroy(h->side_join);
   delete h;
 }
 
@@ -2047,6 +2068,7 @@ int cfm_set_option(cfm_handle* h, const char* key, int32_t value) {
   else if (strcmp(key, "pair_n256") == 0) h->pair_n256 = value != 0;
   else if (strcmp(key, "ff_fused") == 0) h->ff_fused = value != 0;
   else if (strcmp(key, "rowln") == 0 && value >= 0 && value <= 2) h->rowln = value;
+  else if (strcmp(key, "res_side") == 0) h->res_side = value < 0 ? -1 : value != 0;
   else if (strcmp(key, "attn_persist") == 0) h->attn_persist = value != 0;
   else if (strcmp(key, "fp32_tc") == 0) h->fp32_tc = value != 0;
   else if (strcmp(key, "rowln_ff2") == 0) h->rowln_ff2 = value != 0;
