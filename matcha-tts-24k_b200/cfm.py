@@ -184,9 +184,11 @@ class CFM(torch.nn.Module):
         return [float(v) for v in t_span.detach().to(torch.float32).cpu().tolist()]
 
     @torch.inference_mode()
-    def solve(self, x, t_span, mu, mask, lengths=None, spks=None):
+    def solve(self, x, t_span, mu, mask, lengths=None, spks=None, out=None):
         """reference flow_matching.py:60-63; ``x`` is the injected initial state z.  ``spks`` (B, S): upstream-style
-        speaker conditioning, only for an estimator built with in_channels = 2*n_feats + S."""
+        speaker conditioning, only for an estimator built with in_channels = 2*n_feats + S.  ``out``: optional result tensor
+        (same shape, fp32, contiguous, same device): a caller that queues decodes back to back avoids a fresh allocation per
+        call (with torch's caching allocator that can be a blocking cudaMalloc, see bench.py)."""
         mu_, x_ = self._prep(mu), self._prep(x)
         B, F, T = self._check_shapes(mu_, x_)
         spks_ = self._check_spks(spks, B, prep=True)
@@ -195,7 +197,10 @@ class CFM(torch.nn.Module):
         lengths = self._check_lengths(lengths if lengths is not None else lengths_from_mask(mask), B, T)
         ts = self._t_list(t_span)
         lib, handle = self._ensure(mu_.device, lengths, T, ts, self.solver)
-        out = torch.empty_like(mu_)
+        if out is None:
+            out = torch.empty_like(mu_)
+        elif (out.device != mu_.device or out.dtype != torch.float32 or tuple(out.shape) != tuple(mu_.shape) or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous fp32 tensor of mu's shape on mu's device")
         stream = torch.cuda.current_stream(mu_.device).cuda_stream
         N.check(lib, handle, lib.cfm_set_speakers(handle, spks_.data_ptr() if spks_ is not None else None))
         N.check(lib, handle, lib.cfm_solve(handle, mu_.data_ptr(), x_.data_ptr(), out.data_ptr(), stream))

@@ -218,6 +218,22 @@ def test_fp32_on_the_tensor_pipe_matches_oracle_and_fp32_reference(dec, lengths,
     m.close()
 
 
+def test_solve_into_a_caller_owned_result_tensor():
+    """CFM.solve(..., out=): the result lands in the caller's tensor (no allocation per call); wrong shapes / devices raise."""
+    ora, m = pair(SMALL, precision="fp32")
+    mu, mask, z, _ = syn.make_inputs([90, 41], seed=64)
+    ts = torch.linspace(0, 1, 3)
+    ref = ora.solve(z, ts, mu, mask)
+    out = torch.full_like(mu, float("nan")).cuda()
+    res = m.solve(z.cuda(), ts, mu.cuda(), mask.cuda(), out=out)
+    assert res is out and rel_l2(out.cpu(), ref) <= 2e-5
+    with pytest.raises(ValueError):
+        m.solve(z.cuda(), ts, mu.cuda(), mask.cuda(), out=torch.empty(1, 100, 8, device="cuda"))
+    with pytest.raises(ValueError):
+        m.solve(z.cuda(), ts, mu.cuda(), mask.cuda(), out=torch.empty_like(mu))
+    m.close()
+
+
 def _sharded_case(devices):
     lengths = [120, 64, 97, 33, 150, 88, 140]
     ora, single = pair(SMALL, precision="fp32")
